@@ -1,0 +1,442 @@
+// ar.cu -- AR stage driver: loader, prefill, KV-cached decode step, latent pass.
+// Reference: autoregressive_model_load (main.cpp:482-897), autoregressive_graph
+// (main.cpp:2545-3040), autoregressive_latent_graph (main.cpp:2053-2519) and the graph
+// launches inside autoregressive() (main.cpp:5186, 5247, 5342).
+#include <set>
+
+#include "ar_kernels.cuh"
+#include "engine.h"
+#include "gemm.cuh"
+#include "wsgemv.cuh"
+
+namespace tts {
+
+static size_t wbytes(int dtype) { return dtype == TTS_DTYPE_F16 ? 2 : 4; }
+
+// file tensor [K][N] (GPT-2 Conv1D, "in x out") or [N][K] -> device [N][K] in the AR dtype
+static void *upload_matrix(tts_ctx *c, const Container &ct, const std::string &name, int N, int K,
+                           bool file_is_kn) {
+  auto it = ct.tensors.find(name);
+  if (it == ct.tensors.end()) throw ArgError("tensor '" + name + "' missing from " + ct.path, TTS_EIO);
+  const auto &ne = it->second.ne;
+  const int want0 = file_is_kn ? N : K, want1 = file_is_kn ? K : N;  // ne[0] is the fastest dim
+  if (it->second.nelem != size_t(N) * K || ne[0] != want0 || (ne.size() > 1 ? ne[1] : 1) != want1)
+    throw ArgError("tensor '" + name + "' has wrong shape in model file", TTS_EIO);
+  size_t n = 0;
+  read_tensor_to_staging(c, ct, name, &n);
+  void *d = nullptr;
+  TTS_CUDA_TRY(cudaMalloc(&d, n * wbytes(c->cfg.dtype)));
+  if (file_is_kn) {
+    dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
+    if (c->cfg.dtype == TTS_DTYPE_F16)
+      transpose_convert_kernel<__half><<<grid, block, 0, c->stream>>>(c->d_scratch, (__half *)d, K, N);
+    else
+      transpose_convert_kernel<float><<<grid, block, 0, c->stream>>>(c->d_scratch, (float *)d, K, N);
+  } else {
+    if (c->cfg.dtype == TTS_DTYPE_F16)
+      convert_kernel<__half><<<1024, 256, 0, c->stream>>>(c->d_scratch, (__half *)d, n);
+    else
+      convert_kernel<float><<<1024, 256, 0, c->stream>>>(c->d_scratch, (float *)d, n);
+  }
+  TTS_CUDA_TRY(cudaGetLastError());
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->ar.decode_weight_bytes += n * wbytes(c->cfg.dtype);
+  return d;
+}
+
+void ar_load(tts_ctx *c, const char *path) {
+  Container ct;
+  std::string err;
+  if (!ct.open(path, err)) throw ArgError(err, TTS_EIO);
+  ArModel &m = c->ar;
+  m.dtype = c->cfg.dtype;
+  m.decode_weight_bytes = 0;
+  std::set<std::string> known;
+  auto f32 = [&](const std::string &n, std::vector<int> ne) {
+    known.insert(n);
+    return upload_f32(c, ct, n, ne);
+  };
+  auto mat = [&](const std::string &n, int N, int K, bool kn) {
+    known.insert(n);
+    return upload_matrix(c, ct, n, N, K, kn);
+  };
+  for (int i = 0; i < kLayers; ++i) {
+    const std::string p = "inference_model.transformer.h." + std::to_string(i) + ".";
+    ArLayer &l = m.layers[i];
+    l.ln1_w = f32(p + "ln_1.weight", {1024});
+    l.ln1_b = f32(p + "ln_1.bias", {1024});
+    l.w_qkv = mat(p + "attn.c_attn.weight", 3072, 1024, true);
+    l.b_qkv = f32(p + "attn.c_attn.bias", {3072});
+    l.w_proj = mat(p + "attn.c_proj.weight", 1024, 1024, true);
+    l.b_proj = f32(p + "attn.c_proj.bias", {1024});
+    l.ln2_w = f32(p + "ln_2.weight", {1024});
+    l.ln2_b = f32(p + "ln_2.bias", {1024});
+    l.w_fc = mat(p + "mlp.c_fc.weight", 4096, 1024, true);
+    l.b_fc = f32(p + "mlp.c_fc.bias", {4096});
+    l.w_proj2 = mat(p + "mlp.c_proj.weight", 1024, 4096, true);
+    l.b_proj2 = f32(p + "mlp.c_proj.bias", {1024});
+  }
+  m.lnf_w = f32("inference_model.transformer.ln_f.weight", {1024});
+  m.lnf_b = f32("inference_model.transformer.ln_f.bias", {1024});
+  m.lm0_w = f32("inference_model.lm_head.0.weight", {1024});
+  m.lm0_b = f32("inference_model.lm_head.0.bias", {1024});
+  m.lm_w = mat("inference_model.lm_head.1.weight", kMelVocab, 1024, false);
+  m.lm_b = f32("inference_model.lm_head.1.bias", {kMelVocab});
+  m.text_emb = f32("text_embedding.weight", {1024, 256});
+  m.text_pos = f32("text_pos_embedding.emb.weight", {1024, 404});
+  m.mel_emb = f32("mel_embedding.weight", {1024, kMelVocab});
+  m.mel_pos = f32("mel_pos_embedding.emb.weight", {1024, 608});
+  for (const auto &n : ct.order)
+    if (!known.count(n)) throw ArgError("unknown tensor '" + n + "' in model file", TTS_EIO);  // main.cpp:834-838
+
+  // decode-state buffers
+  ArState &s = c->ars;
+  s.Bmax = c->cfg.max_batch;
+  s.P = c->cfg.max_positions;
+  const size_t B = s.Bmax;
+  TTS_CUDA_TRY(cudaMalloc(&s.h, B * kDim * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.q, B * kDim * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.attn, B * kDim * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.m, B * kFF * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.logits, B * kMelVocab * 4));
+  const size_t kv = size_t(kLayers) * B * kHeads * s.P * kHeadDim;
+  TTS_CUDA_TRY(cudaMalloc(&s.kc, kv * 2));
+  TTS_CUDA_TRY(cudaMalloc(&s.vc, kv * 2));
+  TTS_CUDA_TRY(cudaMalloc(&s.d_tokens, B * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.d_state, 16));
+  TTS_CUDA_TRY(cudaMallocHost(&s.h_tokens, B * 4));
+  TTS_CUDA_TRY(cudaMallocHost(&s.h_state, 16));
+  TTS_CUDA_TRY(cudaMallocHost(&s.h_logits, B * kMelVocab * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.d_text, 1024 * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.d_voice, kDim * 4));
+  m.loaded = true;
+}
+
+void ar_free(tts_ctx *c) {
+  ArState &s = c->ars;
+  if (s.step_graph) cudaGraphExecDestroy(s.step_graph);
+  s.step_graph = nullptr;
+  // device memory is released wholesale by cudaDeviceReset-free teardown in tts_free
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename WT>
+static void launch_gemv_t(tts_ctx *c, const Launcher &L, const GemvArgs &a) {
+  const size_t smem = gemv_smem_bytes();
+  static bool attr_done[2][2] = {{false, false}, {false, false}};
+  auto k1 = wsgemv_kernel<WT, 1>;
+  auto k2 = wsgemv_kernel<WT, 2>;
+  const int wi = sizeof(WT) == 4 ? 0 : 1;
+  if (!attr_done[wi][0]) {
+    TTS_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    TTS_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_done[wi][0] = true;
+  }
+  const int G = c->num_sms;
+  if ((a.N + G - 1) / G > GV_MAX_ROWS_PER_CTA) throw ArgError("gemv: too many rows per CTA");
+  if (a.B == 1)
+    L(k1, dim3(G), dim3(GV_THREADS), smem, a);
+  else
+    L(k2, dim3(G), dim3(GV_THREADS), smem, a);
+}
+static void launch_gemv(tts_ctx *c, const Launcher &L, const GemvArgs &a) {
+  if (c->ar.dtype == TTS_DTYPE_F16) launch_gemv_t<__half>(c, L, a);
+  else launch_gemv_t<float>(c, L, a);
+}
+
+static GemvArgs gemv_args(const void *W, const float *bias, const float *in, float *out, int N, int K, int B,
+                          int pro, int epi) {
+  GemvArgs a{};
+  a.W = W; a.bias = bias; a.in = in; a.out = out; a.N = N; a.K = K; a.B = B; a.pro = pro; a.epi = epi;
+  return a;
+}
+
+static void launch_sgemm(tts_ctx *c, const Launcher &L, const float *A, const void *W, const float *bias,
+                         float *C, int M, int N, int K, int lda, int ldc, int epi) {
+  GemmArgs g{A, W, bias, C, M, N, K, lda, ldc, epi};
+  dim3 grid((N + 127) / 128, (M + 127) / 128);
+  if (c->ar.dtype == TTS_DTYPE_F16) L(sgemm_tn_kernel<__half>, grid, dim3(256), 0, g);
+  else L(sgemm_tn_kernel<float>, grid, dim3(256), 0, g);
+}
+
+// The lm-head on decode-shaped activations: logits = W . LN(LN(h) wf + bf) w0 + b0 (A-1)
+static void enqueue_lm_head(tts_ctx *c, const Launcher &L, int B) {
+  ArModel &m = c->ar;
+  ArState &s = c->ars;
+  GemvArgs a = gemv_args(m.lm_w, m.lm_b, s.h, s.logits, kMelVocab, kDim, B, PRO_LN2, EPI_STORE);
+  a.ln_w = m.lnf_w; a.ln_b = m.lnf_b; a.ln2_w = m.lm0_w; a.ln2_b = m.lm0_b;
+  launch_gemv(c, L, a);
+}
+
+// All launches of one decode step (after tokens/state are on the device).
+static void enqueue_step(tts_ctx *c, const Launcher &L, int B) {
+  ArModel &m = c->ar;
+  ArState &s = c->ars;
+  L(ar_embed_decode_kernel, dim3(B), dim3(256), 0, (const int *)s.d_tokens, (const int *)s.d_state,
+    (const float *)m.mel_emb, (const float *)m.mel_pos, s.h);
+  const int kvb = kHeads * s.P * kHeadDim;
+  const size_t layer_kv = size_t(s.Bmax) * kvb;
+  const size_t attn_smem = size_t(s.P + 128) * sizeof(float);
+  for (int i = 0; i < kLayers; ++i) {
+    ArLayer &l = m.layers[i];
+    GemvArgs a = gemv_args(l.w_qkv, l.b_qkv, s.h, s.q, 3072, kDim, B, PRO_LN, EPI_QKV);
+    a.ln_w = l.ln1_w; a.ln_b = l.ln1_b;
+    a.kcache = s.kc + i * layer_kv; a.vcache = s.vc + i * layer_kv;
+    a.state = s.d_state; a.kv_b_stride = kvb;
+    launch_gemv(c, L, a);
+    L(ar_attn_decode_kernel, dim3(kHeads, B), dim3(128), attn_smem, (const float *)s.q,
+      (const __half *)(s.kc + i * layer_kv), (const __half *)(s.vc + i * layer_kv), s.attn,
+      (const int *)s.d_state, s.P);
+    launch_gemv(c, L, gemv_args(l.w_proj, l.b_proj, s.attn, s.h, kDim, kDim, B, PRO_NONE, EPI_RESID));
+    GemvArgs f = gemv_args(l.w_fc, l.b_fc, s.h, s.m, kFF, kDim, B, PRO_LN, EPI_GELU16);
+    f.ln_w = l.ln2_w; f.ln_b = l.ln2_b;
+    launch_gemv(c, L, f);
+    launch_gemv(c, L, gemv_args(l.w_proj2, l.b_proj2, s.m, s.h, kDim, kFF, B, PRO_NONE, EPI_RESID));
+  }
+  enqueue_lm_head(c, L, B);
+}
+
+static void ensure_rows(tts_ctx *c, size_t rows) {
+  ArState &s = c->ars;
+  if (rows <= s.rows_cap) return;
+  for (float **p : {&s.H, &s.A, &s.QKV, &s.ATT, &s.M})
+    if (*p) cudaFree(*p);
+  TTS_CUDA_TRY(cudaMalloc(&s.H, rows * kDim * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.A, rows * kDim * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.QKV, rows * 3072 * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.ATT, rows * kDim * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.M, rows * kFF * 4));
+  s.rows_cap = rows;
+}
+
+// 30 transformer layers over nb sequences of R rows each (H in/out).  If kv_B > 0 the
+// K/V rows (single sequence) are also scattered into the decode cache of kv_B candidates.
+static void enqueue_rows_layers(tts_ctx *c, const Launcher &L, int nb, int R, int kv_B) {
+  ArModel &m = c->ar;
+  ArState &s = c->ars;
+  const int rows = nb * R;
+  const size_t layer_kv = size_t(s.Bmax) * kHeads * s.P * kHeadDim;
+  for (int i = 0; i < kLayers; ++i) {
+    ArLayer &l = m.layers[i];
+    L(ln_rows_kernel, dim3(rows), dim3(256), 0, (const float *)s.H, s.A, (const float *)l.ln1_w,
+      (const float *)l.ln1_b, (const float *)nullptr, (const float *)nullptr, kDim, kDim);
+    launch_sgemm(c, L, s.A, l.w_qkv, l.b_qkv, s.QKV, rows, 3072, kDim, kDim, 3072, E_BIAS_H16);
+    if (kv_B > 0)
+      L(ar_kv_scatter_kernel, dim3(R), dim3(256), 0, (const float *)s.QKV, s.kc + i * layer_kv,
+        s.vc + i * layer_kv, R, kv_B, s.P);
+    L(ar_attn_causal_kernel, dim3((R + 15) / 16, kHeads, nb), dim3(128), 0, (const float *)s.QKV, s.ATT, R);
+    launch_sgemm(c, L, s.ATT, l.w_proj, l.b_proj, s.H, rows, kDim, kDim, kDim, kDim, E_BIAS_RESID);
+    L(ln_rows_kernel, dim3(rows), dim3(256), 0, (const float *)s.H, s.A, (const float *)l.ln2_w,
+      (const float *)l.ln2_b, (const float *)nullptr, (const float *)nullptr, kDim, kDim);
+    launch_sgemm(c, L, s.A, l.w_fc, l.b_fc, s.M, rows, kFF, kDim, kDim, kFF, E_BIAS_GELU16);
+    launch_sgemm(c, L, s.M, l.w_proj2, l.b_proj2, s.H, rows, kDim, kFF, kFF, kDim, E_BIAS_RESID);
+  }
+}
+
+void ar_prefill(tts_ctx *c, const int32_t *text, int T, const float *voice, int B, float *logits_out) {
+  ArModel &m = c->ar;
+  ArState &s = c->ars;
+  if (!m.loaded) throw ArgError("AR model not loaded");
+  if (B < 1 || B > s.Bmax) throw ArgError("batch exceeds max_batch", TTS_ELIMIT);
+  if (T < 1 || T > 404) throw ArgError("text longer than the 404 text positions (main.cpp:685-689)", TTS_ELIMIT);
+  const int R = T + 2;
+  if (R >= s.P) throw ArgError("prompt does not fit max_positions", TTS_ELIMIT);
+  for (int j = 0; j < T; ++j)
+    if (text[j] < 0 || text[j] > 255) throw ArgError("text token out of range");
+  ensure_rows(c, R);
+  Launcher L{c->stream, c->use_pdl, &c->launches};
+  TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.d_text, text, T * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.d_voice, voice, kDim * 4, cudaMemcpyHostToDevice, c->stream));
+  // mel part of the prefill row set: one start token (8192) at mel position 0 (A-4)
+  s.h_tokens[0] = TTS_MEL_START;
+  s.h_state[0] = 0;
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.d_tokens, s.h_tokens, 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.d_state, s.h_state, 4, cudaMemcpyHostToDevice, c->stream));
+  // (d_state[0] doubles as the all-zero mel position table for the single start token)
+  L(ar_embed_rows_kernel, dim3(R, 1), dim3(256), 0, (const int *)s.d_text, T, (const float *)s.d_voice,
+    (const int *)s.d_tokens, (const int *)s.d_state, 1, (const float *)m.text_emb, (const float *)m.text_pos,
+    (const float *)m.mel_emb, (const float *)m.mel_pos, s.H);
+  enqueue_rows_layers(c, L, 1, R, B);
+  L(bcast_row_kernel, dim3(B), dim3(256), 0, (const float *)(s.H + size_t(R - 1) * kDim), s.h, kDim);
+  enqueue_lm_head(c, L, B);
+  if (logits_out)
+    TTS_CUDA_TRY(cudaMemcpyAsync(s.h_logits, s.logits, size_t(B) * kMelVocab * 4, cudaMemcpyDeviceToHost, c->stream));
+  TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  if (logits_out) memcpy(logits_out, s.h_logits, size_t(B) * kMelVocab * 4);
+  s.B = B;
+  s.T = T;
+  s.n_past = R;
+}
+
+static void build_step_graph(tts_ctx *c, int B) {
+  ArState &s = c->ars;
+  if (s.step_graph) {
+    cudaGraphExecDestroy(s.step_graph);
+    s.step_graph = nullptr;
+  }
+  cudaGraph_t graph;
+  int64_t dummy = 0;
+  Launcher L{c->stream, c->use_pdl, &dummy};
+  TTS_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  try {
+    TTS_CUDA_TRY(cudaMemcpyAsync(s.d_tokens, s.h_tokens, B * 4, cudaMemcpyHostToDevice, c->stream));
+    TTS_CUDA_TRY(cudaMemcpyAsync(s.d_state, s.h_state, 8, cudaMemcpyHostToDevice, c->stream));
+    enqueue_step(c, L, B);
+    TTS_CUDA_TRY(cudaMemcpyAsync(s.h_logits, s.logits, size_t(B) * kMelVocab * 4, cudaMemcpyDeviceToHost, c->stream));
+  } catch (...) {
+    cudaGraph_t g2;
+    cudaStreamEndCapture(c->stream, &g2);
+    throw;
+  }
+  TTS_CUDA_TRY(cudaStreamEndCapture(c->stream, &graph));
+  TTS_CUDA_TRY(cudaGraphInstantiate(&s.step_graph, graph, 0));
+  cudaGraphDestroy(graph);
+  s.step_graph_B = B;
+}
+
+void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, bool sync_out) {
+  ArState &s = c->ars;
+  if (!c->ar.loaded || s.B == 0) throw ArgError("tts_ar_step before tts_ar_prefill");
+  if (s.n_past + 1 > s.P) throw ArgError("KV cache full (reference limit: 404 slots, main.cpp:794-797)", TTS_ELIMIT);
+  if (pos_id < 0 || pos_id >= 608) throw ArgError("mel position id out of range (608 rows)", TTS_ELIMIT);
+  const int B = s.B;
+  for (int b = 0; b < B; ++b) {
+    if (tokens[b] < 0 || tokens[b] >= kMelVocab) throw ArgError("mel token out of range");
+    s.h_tokens[b] = tokens[b];
+  }
+  s.h_state[0] = s.n_past;
+  s.h_state[1] = pos_id;
+  const int launches_per_step = 2 + kLayers * 5;
+  TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  if (c->use_graph) {
+    if (!s.step_graph || s.step_graph_B != B) build_step_graph(c, B);
+    TTS_CUDA_TRY(cudaGraphLaunch(s.step_graph, c->stream));
+    c->launches += launches_per_step;
+  } else {
+    Launcher L{c->stream, c->use_pdl, &c->launches};
+    TTS_CUDA_TRY(cudaMemcpyAsync(s.d_tokens, s.h_tokens, B * 4, cudaMemcpyHostToDevice, c->stream));
+    TTS_CUDA_TRY(cudaMemcpyAsync(s.d_state, s.h_state, 8, cudaMemcpyHostToDevice, c->stream));
+    enqueue_step(c, L, B);
+    TTS_CUDA_TRY(cudaMemcpyAsync(s.h_logits, s.logits, size_t(B) * kMelVocab * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  s.n_past += 1;
+  if (sync_out) {
+    TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    if (logits_out) memcpy(logits_out, s.h_logits, size_t(B) * kMelVocab * 4);
+  }
+}
+
+// Latent pass.  Reference quirk A-4: the mel position table is only written for
+// index < 502*B/4 per candidate slot (main.cpp:5326-5333); the rest stays zero.
+void ar_latents(tts_ctx *c, const int32_t *text, int T, const float *voice, const int32_t *codes, int B,
+                int n_keep, float *out) {
+  ArModel &m = c->ar;
+  ArState &s = c->ars;
+  if (!m.loaded) throw ArgError("AR model not loaded");
+  if (B < 1 || B > s.Bmax) throw ArgError("batch exceeds max_batch", TTS_ELIMIT);
+  if (n_keep < 1 || n_keep > 500) throw ArgError("n_keep must be in [1,500]");
+  if (T < 1 || T > 404) throw ArgError("text too long", TTS_ELIMIT);
+  const int n_mel = n_keep;  // causal: mel rows beyond n_keep-1 cannot influence kept latents
+  const int R = 1 + T + n_mel;
+  // process candidates in chunks so the row buffers stay bounded
+  const int chunk = std::max(1, std::min(B, 8192 / R));
+  ensure_rows(c, size_t(chunk) * R);
+  std::vector<int> pos(size_t(B) * 502, 0), h_codes(size_t(B) * n_mel), h_pos(size_t(B) * n_mel);
+  if (c->cfg.parity_quirks) {
+    const int per = 502 * B / 4;
+    for (int i = 0; i < B; ++i)
+      for (int cc = 0; cc < per; ++cc) {
+        const size_t idx = size_t(i) * per + cc;
+        if (idx < pos.size()) pos[idx] = cc;
+      }
+  } else {
+    for (int b = 0; b < B; ++b)
+      for (int j = 0; j < 502; ++j) pos[size_t(b) * 502 + j] = j;
+  }
+  for (int b = 0; b < B; ++b)
+    for (int j = 0; j < n_mel; ++j) {
+      const int code = codes[size_t(b) * 502 + j];
+      if (code < 0 || code >= kMelVocab) throw ArgError("mel code out of range");
+      h_codes[size_t(b) * n_mel + j] = code;
+      h_pos[size_t(b) * n_mel + j] = pos[size_t(b) * 502 + j];
+    }
+  if (!s.d_codes) {
+    TTS_CUDA_TRY(cudaMalloc(&s.d_codes, size_t(s.Bmax) * 502 * 4));
+    TTS_CUDA_TRY(cudaMalloc(&s.d_pos, size_t(s.Bmax) * 502 * 4));
+  }
+  Launcher L{c->stream, c->use_pdl, &c->launches};
+  TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.d_text, text, T * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.d_voice, voice, kDim * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.d_codes, h_codes.data(), h_codes.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.d_pos, h_pos.data(), h_pos.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  memset(out, 0, size_t(B) * 500 * kDim * 4);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    L(ar_embed_rows_kernel, dim3(R, nb), dim3(256), 0, (const int *)s.d_text, T, (const float *)s.d_voice,
+      (const int *)(s.d_codes + size_t(b0) * n_mel), (const int *)(s.d_pos + size_t(b0) * n_mel), n_mel,
+      (const float *)m.text_emb, (const float *)m.text_pos, (const float *)m.mel_emb,
+      (const float *)m.mel_pos, s.H);
+    enqueue_rows_layers(c, L, nb, R, 0);
+    // z = LN(LN(h) ln_f) lm_head.0  (main.cpp:2475-2499), all rows; mel rows are copied out
+    L(ln_rows_kernel, dim3(nb * R), dim3(256), 0, (const float *)s.H, s.A, (const float *)m.lnf_w,
+      (const float *)m.lnf_b, (const float *)m.lm0_w, (const float *)m.lm0_b, kDim, kDim);
+    for (int b = 0; b < nb; ++b)
+      TTS_CUDA_TRY(cudaMemcpyAsync(out + size_t(b0 + b) * 500 * kDim, s.A + (size_t(b) * R + 1 + T) * kDim,
+                                   size_t(n_mel) * kDim * 4, cudaMemcpyDeviceToHost, c->stream));
+    TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+  TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+}
+
+// Streaming-GEMV micro-benchmark over the 30 layers' weights (larger than L2 in total, so
+// every launch streams from HBM): average launch time from CUDA events on the stream.
+void ar_bench_gemv(tts_ctx *c, int op, int B, int iters, float *ms, double *bytes) {
+  ArModel &m = c->ar;
+  ArState &s = c->ars;
+  if (!m.loaded) throw ArgError("AR model not loaded");
+  if (B < 1 || B > s.Bmax) throw ArgError("bad B");
+  int64_t dummy = 0;
+  Launcher L{c->stream, c->use_pdl, &dummy};
+  TTS_CUDA_TRY(cudaMemsetAsync(s.h, 0, size_t(B) * kDim * 4, c->stream));
+  TTS_CUDA_TRY(cudaMemsetAsync(s.m, 0, size_t(B) * kFF * 4, c->stream));
+  TTS_CUDA_TRY(cudaMemsetAsync(s.d_state, 0, 16, c->stream));
+  int N = 0, K = 0;
+  auto one = [&](int layer) {
+    ArLayer &l = m.layers[layer % kLayers];
+    GemvArgs a{};
+    switch (op) {
+      case 0: a = gemv_args(l.w_qkv, l.b_qkv, s.h, s.q, 3072, kDim, B, PRO_LN, EPI_QKV);
+        a.ln_w = l.ln1_w; a.ln_b = l.ln1_b; a.kcache = s.kc; a.vcache = s.vc; a.state = s.d_state;
+        a.kv_b_stride = kHeads * s.P * kHeadDim; break;
+      case 1: a = gemv_args(l.w_proj, l.b_proj, s.attn, s.q, kDim, kDim, B, PRO_NONE, EPI_STORE); break;
+      case 2: a = gemv_args(l.w_fc, l.b_fc, s.h, s.m, kFF, kDim, B, PRO_LN, EPI_GELU16);
+        a.ln_w = l.ln2_w; a.ln_b = l.ln2_b; break;
+      case 3: a = gemv_args(l.w_proj2, l.b_proj2, s.m, s.q, kDim, kFF, B, PRO_NONE, EPI_STORE); break;
+      default: throw ArgError("bad op");
+    }
+    N = a.N; K = a.K;
+    launch_gemv(c, L, a);
+  };
+  for (int i = 0; i < kLayers; ++i) one(i);  // warm-up, also evicts L2 with 30 distinct matrices
+  TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  for (int i = 0; i < iters; ++i) one(i);
+  TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  float t = 0;
+  TTS_CUDA_TRY(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+  *ms = t / iters;
+  // algorithmic bytes of one launch: K*N*s_w + B*K*4 (activations) + B*N*4 (outputs) + N*4 (bias)
+  *bytes = double(N) * K * wbytes(m.dtype) + double(B) * K * 4 + double(B) * N * 4 + double(N) * 4;
+  c->launches += iters + kLayers;
+}
+
+}  // namespace tts

@@ -1,0 +1,316 @@
+// ar_kernels.cuh -- non-GEMV kernels of the AR stage (embedding, attention, LayerNorm rows).
+#pragma once
+#include "common.cuh"
+
+namespace tts {
+
+// h[b] = mel_emb[tok[b]] + mel_pos[pos_id]      (decode input, main.cpp:2668-2691)
+__global__ void __launch_bounds__(256) ar_embed_decode_kernel(const int *tokens, const int *state,
+                                                              const float *mel_emb, const float *mel_pos,
+                                                              float *h) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int tok = tokens[b], pos = state[1];
+  const float4 e = reinterpret_cast<const float4 *>(mel_emb + size_t(tok) * kDim)[t];
+  const float4 p = reinterpret_cast<const float4 *>(mel_pos + size_t(pos) * kDim)[t];
+  reinterpret_cast<float4 *>(h + size_t(b) * kDim)[t] = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+}
+
+// Rows of the prefill / latent input (main.cpp:2586-2666 and 2076-2165):
+//   row 0            = voice conditioning latent
+//   rows 1..T        = text_emb[tok_j] + text_pos[j]
+//   rows T+1..       = mel_emb[code] + mel_pos[p]
+// codes/pos are per candidate ([B][n_mel]); text is shared.
+__global__ void __launch_bounds__(256) ar_embed_rows_kernel(const int *text, int T, const float *voice,
+                                                            const int *codes, const int *mel_positions,
+                                                            int n_mel, const float *text_emb,
+                                                            const float *text_pos, const float *mel_emb,
+                                                            const float *mel_pos, float *H) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int R = 1 + T + n_mel;
+  const int row = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  float4 v;
+  if (row == 0) {
+    v = reinterpret_cast<const float4 *>(voice)[t];
+  } else if (row <= T) {
+    const int j = row - 1;
+    const float4 e = reinterpret_cast<const float4 *>(text_emb + size_t(text[j]) * kDim)[t];
+    const float4 p = reinterpret_cast<const float4 *>(text_pos + size_t(j) * kDim)[t];
+    v = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+  } else {
+    const int j = row - 1 - T;
+    const int code = codes[b * n_mel + j], pos = mel_positions[b * n_mel + j];
+    const float4 e = reinterpret_cast<const float4 *>(mel_emb + size_t(code) * kDim)[t];
+    const float4 p = reinterpret_cast<const float4 *>(mel_pos + size_t(pos) * kDim)[t];
+    v = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+  }
+  reinterpret_cast<float4 *>(H + (size_t(b) * R + row) * kDim)[t] = v;
+}
+
+// y = LN(x) * w + b per row of 1024 (eps 1e-5, double accumulation, ggml.c:11905-11958);
+// optional second parameterised LN on top (the "double final norm", SURVEY A-1).
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float *X, float *Y, const float *w1,
+                                                      const float *b1, const float *w2, const float *b2,
+                                                      int ldx, int ldy) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ double red[8];
+  const int row = blockIdx.x, t = threadIdx.x, warp = t / 32, lane = t % 32;
+  const float4 v = reinterpret_cast<const float4 *>(X + size_t(row) * ldx)[t];
+  float x[4] = {v.x, v.y, v.z, v.w};
+  const int passes = w2 ? 2 : 1;
+  for (int p = 0; p < passes; ++p) {
+    double s = double(x[0]) + double(x[1]) + double(x[2]) + double(x[3]);
+    s = warp_sum_d(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    double tot = 0;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    __syncthreads();
+    const float mean = float(tot / kDim);
+    float d[4];
+    double s2 = 0;
+    for (int i = 0; i < 4; ++i) {
+      d[i] = x[i] - mean;
+      s2 += double(d[i] * d[i]);
+    }
+    s2 = warp_sum_d(s2);
+    if (lane == 0) red[warp] = s2;
+    __syncthreads();
+    tot = 0;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    __syncthreads();
+    const float rstd = 1.0f / sqrtf(float(tot / kDim) + 1e-5f);
+    const float4 w4 = reinterpret_cast<const float4 *>(p == 0 ? w1 : w2)[t];
+    const float4 b4 = reinterpret_cast<const float4 *>(p == 0 ? b1 : b2)[t];
+    x[0] = d[0] * rstd * w4.x + b4.x;
+    x[1] = d[1] * rstd * w4.y + b4.y;
+    x[2] = d[2] * rstd * w4.z + b4.z;
+    x[3] = d[3] * rstd * w4.w + b4.w;
+  }
+  reinterpret_cast<float4 *>(Y + size_t(row) * ldy)[t] = make_float4(x[0], x[1], x[2], x[3]);
+}
+
+// Single-position attention against the f16 KV cache (main.cpp:2828-2886 with
+// test_dimension == 1): scores = q.k/8 over keys 0..n_past, softmax, weighted sum of v.
+// grid (16 heads, B), 128 threads.  K/V: [b][head][pos][64] f16 (the cached values ARE
+// f16-exact in the reference too: they pass through the F16 round trip, A-2).
+__global__ void __launch_bounds__(128) ar_attn_decode_kernel(const float *q, const __half *kc,
+                                                             const __half *vc, float *out,
+                                                             const int *state, int P) {
+  extern __shared__ float sc[];  // [n] scores, then 2*64 partial outputs
+  __shared__ float qs[kHeadDim];
+  __shared__ float redf[4];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int head = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t / 32, lane = t % 32;
+  const int n = state[0] + 1;
+  if (t < kHeadDim) qs[t] = q[size_t(b) * kDim + head * kHeadDim + t];
+  __syncthreads();
+  const __half *K = kc + (size_t(b) * kHeads + head) * size_t(P) * kHeadDim;
+  const __half *V = vc + (size_t(b) * kHeads + head) * size_t(P) * kHeadDim;
+  float lmax = -INFINITY;
+  for (int j = t; j < n; j += 128) {
+    const uint4 *kr = reinterpret_cast<const uint4 *>(K + size_t(j) * kHeadDim);
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = kr[c];
+      const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        dot = fmaf(qs[c * 8 + 2 * e], f.x, dot);
+        dot = fmaf(qs[c * 8 + 2 * e + 1], f.y, dot);
+      }
+    }
+    dot *= 0.125f;
+    sc[j] = dot;
+    lmax = fmaxf(lmax, dot);
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) redf[warp] = lmax;
+  __syncthreads();
+  const float mx = fmaxf(fmaxf(redf[0], redf[1]), fmaxf(redf[2], redf[3]));
+  __syncthreads();
+  float lsum = 0.f;
+  for (int j = t; j < n; j += 128) {
+    const float p = expf(sc[j] - mx);
+    sc[j] = p;
+    lsum += p;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) redf[warp] = lsum;
+  __syncthreads();
+  const float inv = float(1.0 / (double(redf[0]) + double(redf[1]) + double(redf[2]) + double(redf[3])));
+  // PV: thread -> (dim d, key parity half)
+  const int d = t % kHeadDim, half = t / kHeadDim;
+  float acc = 0.f;
+  for (int j = half; j < n; j += 2) acc = fmaf(sc[j] * inv, __half2float(V[size_t(j) * kHeadDim + d]), acc);
+  float *po = sc + n;
+  po[half * kHeadDim + d] = acc;
+  __syncthreads();
+  if (t < kHeadDim) out[size_t(b) * kDim + head * kHeadDim + t] = po[t] + po[kHeadDim + t];
+}
+
+// Causal self-attention over full rows (prefill and latent pass; main.cpp:2275-2330 /
+// 2828-2886 with n_past == 0).  QKV: [b][R][3072] f32 (already f16-rounded values).
+// grid (ceil(R/16), 16 heads, B), 128 threads = 4 warps, each warp 4 query rows.
+// Keys are staged through shared memory in tiles of 64; lane <-> key; online softmax.
+__global__ void __launch_bounds__(128) ar_attn_causal_kernel(const float *QKV, float *out, int R) {
+  constexpr int TK = 64, LDK = kHeadDim + 4;
+  __shared__ __align__(16) float Ks[TK][LDK];
+  __shared__ __align__(16) float Vs[TK][LDK];
+  __shared__ __align__(16) float Qs[16][kHeadDim];
+  __shared__ float Ps[4][4][TK];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = threadIdx.x, warp = t / 32, lane = t % 32;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * 16;
+  const float *base = QKV + size_t(b) * R * 3072;
+  for (int i = t; i < 16 * kHeadDim; i += 128) {
+    const int r = i / kHeadDim, d = i % kHeadDim;
+    const int qi = q0 + r;
+    Qs[r][d] = qi < R ? base[size_t(qi) * 3072 + head * kHeadDim + d] : 0.f;
+  }
+  float m[4], l[4], o[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[i] = -INFINITY;
+    l[i] = 0.f;
+    o[i][0] = o[i][1] = 0.f;
+  }
+  const int q_last = min(q0 + 15, R - 1);
+  for (int k0 = 0; k0 <= q_last; k0 += TK) {
+    __syncthreads();
+    for (int i = t; i < TK * (kHeadDim / 4); i += 128) {
+      const int r = i / (kHeadDim / 4), c = (i % (kHeadDim / 4)) * 4;
+      const int kj = k0 + r;
+      float4 kv = make_float4(0, 0, 0, 0), vv = kv;
+      if (kj < R) {
+        kv = *reinterpret_cast<const float4 *>(base + size_t(kj) * 3072 + 1024 + head * kHeadDim + c);
+        vv = *reinterpret_cast<const float4 *>(base + size_t(kj) * 3072 + 2048 + head * kHeadDim + c);
+      }
+      *reinterpret_cast<float4 *>(&Ks[r][c]) = kv;
+      *reinterpret_cast<float4 *>(&Vs[r][c]) = vv;
+    }
+    __syncthreads();
+    // scores: lane handles keys lane and lane+32 for the warp's 4 queries
+    float s[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i][0] = s[i][1] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < kHeadDim; c += 4) {
+      const float4 ka = *reinterpret_cast<const float4 *>(&Ks[lane][c]);
+      const float4 kb = *reinterpret_cast<const float4 *>(&Ks[lane + 32][c]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 qv = *reinterpret_cast<const float4 *>(&Qs[warp * 4 + i][c]);
+        s[i][0] += qv.x * ka.x + qv.y * ka.y + qv.z * ka.z + qv.w * ka.w;
+        s[i][1] += qv.x * kb.x + qv.y * kb.y + qv.z * kb.z + qv.w * kb.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int qi = q0 + warp * 4 + i;
+      float s0 = s[i][0] * 0.125f, s1 = s[i][1] * 0.125f;
+      if (k0 + lane > qi || qi >= R) s0 = -INFINITY;
+      if (k0 + lane + 32 > qi || qi >= R) s1 = -INFINITY;
+      const float tmax = warp_max(fmaxf(s0, s1));
+      const float mnew = fmaxf(m[i], tmax);
+      float p0 = 0.f, p1 = 0.f, corr = 1.f;
+      if (mnew != -INFINITY) {
+        p0 = expf(s0 - mnew);
+        p1 = expf(s1 - mnew);
+        corr = expf(m[i] - mnew);
+      }
+      l[i] = l[i] * corr + warp_sum(p0 + p1);
+      o[i][0] *= corr;
+      o[i][1] *= corr;
+      m[i] = mnew;
+      Ps[warp][i][lane] = p0;
+      Ps[warp][i][lane + 32] = p1;
+    }
+    __syncwarp();
+    // PV: lane handles output dims lane and lane+32
+    const int kmax = min(TK, q_last - k0 + 1);
+    for (int j = 0; j < kmax; ++j) {
+      const float v0 = Vs[j][lane], v1 = Vs[j][lane + 32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float p = Ps[warp][i][j];
+        o[i][0] = fmaf(p, v0, o[i][0]);
+        o[i][1] = fmaf(p, v1, o[i][1]);
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qi = q0 + warp * 4 + i;
+    if (qi < R) {
+      const float inv = 1.0f / l[i];
+      float *dst = out + (size_t(b) * R + qi) * kDim + head * kHeadDim;
+      dst[lane] = o[i][0] * inv;
+      dst[lane + 32] = o[i][1] * inv;
+    }
+  }
+}
+
+// Copy K,V of the prefill rows into every candidate's f16 cache:
+// QKV [R][3072] (single shared sequence) -> kc/vc[b][head][pos][64] for b < B.
+__global__ void __launch_bounds__(256) ar_kv_scatter_kernel(const float *QKV, __half *kc, __half *vc, int R,
+                                                            int B, int P) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int pos = blockIdx.x;
+  for (int i = threadIdx.x; i < 1024; i += 256) {
+    const __half k = __float2half_rn(QKV[size_t(pos) * 3072 + 1024 + i]);
+    const __half v = __float2half_rn(QKV[size_t(pos) * 3072 + 2048 + i]);
+    const int head = i / kHeadDim, d = i % kHeadDim;
+    for (int b = 0; b < B; ++b) {
+      const size_t idx = ((size_t(b) * kHeads + head) * P + pos) * kHeadDim + d;
+      kc[idx] = k;
+      vc[idx] = v;
+    }
+  }
+}
+
+// dst[b][:] = src[:] for b < B (broadcast last prefill row to all candidates)
+__global__ void __launch_bounds__(256) bcast_row_kernel(const float *src, float *dst, int n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += 256) dst[size_t(b) * n + i] = src[i];
+}
+
+// transpose + convert at load time:  src f32 [K][N]  ->  dst WT [N][K]
+template <typename WT>
+__global__ void transpose_convert_kernel(const float *src, WT *dst, int K, int N) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? src[size_t(k) * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N && k < K) {
+      if constexpr (sizeof(WT) == 4) dst[size_t(n) * K + k] = tile[threadIdx.x][i];
+      else dst[size_t(n) * K + k] = __float2half_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+template <typename WT>
+__global__ void convert_kernel(const float *src, WT *dst, size_t n) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    if constexpr (sizeof(WT) == 4) dst[i] = src[i];
+    else dst[i] = __float2half_rn(src[i]);
+  }
+}
+
+}  // namespace tts

@@ -1,0 +1,109 @@
+// engine.h -- internal C++ structures behind the C-ABI (include/tortoise_b200.h).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/tortoise_b200.h"
+
+namespace tts {
+
+struct HostTensor {
+  std::vector<int> ne;  // ggml order, ne[0] fastest
+  size_t offset = 0;    // byte offset of the data in the file
+  size_t nelem = 0;
+};
+
+// Container parser shared by the three loaders (format: SURVEY.md App. B,
+// reference parser main.cpp:811-888).
+struct Container {
+  std::string path;
+  std::map<std::string, HostTensor> tensors;
+  std::vector<std::string> order;
+  bool open(const std::string &path, std::string &err);
+};
+
+struct ArLayer {
+  float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  void *w_qkv, *w_proj, *w_fc, *w_proj2;  // [N][K], f32 or f16
+  float *b_qkv, *b_proj, *b_fc, *b_proj2;
+};
+
+struct ArModel {
+  bool loaded = false;
+  int dtype = 0;
+  ArLayer layers[30];
+  float *lnf_w, *lnf_b, *lm0_w, *lm0_b, *lm_b;
+  void *lm_w;  // [8194][1024]
+  float *text_emb, *text_pos, *mel_emb, *mel_pos;
+  size_t decode_weight_bytes = 0;
+};
+
+struct ArState {
+  int Bmax = 0, P = 0;
+  int B = 0, T = 0, n_past = 0;
+  float *h = nullptr, *q = nullptr, *attn = nullptr, *m = nullptr, *logits = nullptr;
+  __half *kc = nullptr, *vc = nullptr;  // [30][Bmax][16][P][64]
+  int *d_tokens = nullptr, *d_state = nullptr;
+  int *h_tokens = nullptr, *h_state = nullptr;  // pinned
+  float *h_logits = nullptr;                    // pinned
+  // row buffers for prefill / latent pass (grown on demand)
+  size_t rows_cap = 0;
+  float *H = nullptr, *A = nullptr, *QKV = nullptr, *ATT = nullptr, *M = nullptr;
+  int *d_text = nullptr, *d_codes = nullptr, *d_pos = nullptr;
+  float *d_voice = nullptr;
+  // CUDA graph of one decode step, keyed by B
+  cudaGraphExec_t step_graph = nullptr;
+  int step_graph_B = 0;
+};
+
+struct DiffModel;
+struct VocModel;
+
+}  // namespace tts
+
+struct tts_ctx {
+  tts_config cfg;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  float last_ms = 0.f;
+  bool use_graph = true;
+  bool use_pdl = true;
+  tts::ArModel ar;
+  tts::ArState ars;
+  tts::DiffModel *diff = nullptr;
+  tts::VocModel *voc = nullptr;
+  float *staging = nullptr;      // pinned host staging for loads
+  size_t staging_bytes = 0;
+  float *d_scratch = nullptr;    // device scratch for load-time conversion
+  size_t d_scratch_bytes = 0;
+};
+
+namespace tts {
+// implemented in ar.cu
+void ar_load(tts_ctx *c, const char *path);
+void ar_prefill(tts_ctx *c, const int32_t *text, int T, const float *voice, int B, float *logits_out);
+void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, bool sync_out);
+void ar_latents(tts_ctx *c, const int32_t *text, int T, const float *voice, const int32_t *codes, int B,
+                int n_keep, float *out);
+void ar_bench_gemv(tts_ctx *c, int op, int B, int iters, float *ms, double *bytes);
+void ar_free(tts_ctx *c);
+// implemented in diffusion.cu / vocoder.cu
+void diff_load(tts_ctx *c, const char *path);
+void diff_eps(tts_ctx *c, const float *latents, int L, const float *x, int S, int timestep, int cond_free,
+              float *out);
+void diff_sample(tts_ctx *c, const float *latents, int L, int S, int n_steps, const float *noise, float *mel);
+void diff_free(tts_ctx *c);
+void voc_load(tts_ctx *c, const char *path);
+void voc_run(tts_ctx *c, const float *mel, int S, const float *noise, float *audio);
+void voc_free(tts_ctx *c);
+// shared helpers (loader.cpp)
+float *upload_f32(tts_ctx *c, const Container &ct, const std::string &name, const std::vector<int> &expect_ne);
+void read_tensor_to_staging(tts_ctx *c, const Container &ct, const std::string &name, size_t *nelem);
+}  // namespace tts
