@@ -219,4 +219,5 @@ def timestep_embedding(t: int, dim: int = 1024, max_period: int = 10000) -> np.n
     i = np.arange(half, dtype=F32)
     freq = np.exp(-math.log(max_period) * i.astype(np.float64) / half).astype(F32)
     arg = (F32(t) * freq).astype(F32)
-    return np.concatenate([np.cos(arg), np.sin(arg)]).astype(F32)
+    a64 = arg.astype(np.float64)  # the reference's cos/sin are the double versions, narrowed afterwards
+    return np.concatenate([np.cos(a64), np.sin(a64)]).astype(F32)

@@ -44,6 +44,20 @@ static void *upload_matrix(tts_ctx *c, const Container &ct, const std::string &n
   return d;
 }
 
+// hi/lo f16 planes of an f32 [N][K] device matrix (parity mode only)
+static void make_planes(tts_ctx *c, const void *w, size_t n, __half **hi, __half **lo) {
+  if (c->cfg.dtype == TTS_DTYPE_F16) {
+    *hi = (__half *)w;
+    *lo = nullptr;
+    return;
+  }
+  TTS_CUDA_TRY(cudaMalloc(hi, n * 2));
+  TTS_CUDA_TRY(cudaMalloc(lo, n * 2));
+  split_f16_kernel<<<1024, 256, 0, c->stream>>>((const float *)w, *hi, *lo, n);
+  TTS_CUDA_TRY(cudaGetLastError());
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+}
+
 void ar_load(tts_ctx *c, const char *path) {
   Container ct;
   std::string err;
@@ -75,6 +89,10 @@ void ar_load(tts_ctx *c, const char *path) {
     l.b_fc = f32(p + "mlp.c_fc.bias", {4096});
     l.w_proj2 = mat(p + "mlp.c_proj.weight", 1024, 4096, true);
     l.b_proj2 = f32(p + "mlp.c_proj.bias", {1024});
+    make_planes(c, l.w_qkv, size_t(3072) * 1024, &l.qkv_hi, &l.qkv_lo);
+    make_planes(c, l.w_proj, size_t(1024) * 1024, &l.proj_hi, &l.proj_lo);
+    make_planes(c, l.w_fc, size_t(4096) * 1024, &l.fc_hi, &l.fc_lo);
+    make_planes(c, l.w_proj2, size_t(1024) * 4096, &l.proj2_hi, &l.proj2_lo);
   }
   m.lnf_w = f32("inference_model.transformer.ln_f.weight", {1024});
   m.lnf_b = f32("inference_model.transformer.ln_f.bias", {1024});
@@ -151,12 +169,18 @@ static GemvArgs gemv_args(const void *W, const float *bias, const float *in, flo
   return a;
 }
 
-static void launch_sgemm(tts_ctx *c, const Launcher &L, const float *A, const void *W, const float *bias,
-                         float *C, int M, int N, int K, int lda, int ldc, int epi) {
-  GemmArgs g{A, W, bias, C, M, N, K, lda, ldc, epi};
-  dim3 grid((N + 127) / 128, (M + 127) / 128);
-  if (c->ar.dtype == TTS_DTYPE_F16) L(sgemm_tn_kernel<__half>, grid, dim3(256), 0, g);
-  else L(sgemm_tn_kernel<float>, grid, dim3(256), 0, g);
+static void launch_tgemm(tts_ctx *c, const Launcher &L, const __half *Ahi, const __half *Alo, const __half *Whi,
+                         const __half *Wlo, const float *bias, float *C, __half *Chi, __half *Clo, int M, int N,
+                         int K, int lda, int ldc, int ldh, int epi) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    TTS_CUDA_TRY(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(tgemm_smem_bytes())));
+    attr_done = true;
+  }
+  TGemmArgs g{Ahi, Alo, Whi, Wlo, bias, C, Chi, Clo, M, N, K, lda, ldc, ldh, epi, 1, 1, 0, 0, M};
+  dim3 grid((N + TG_BN - 1) / TG_BN, (M + TG_BM - 1) / TG_BM);
+  L(tgemm_kernel, grid, dim3(128), tgemm_smem_bytes(), g);
 }
 
 // The lm-head on decode-shaped activations: logits = W . LN(LN(h) wf + bf) w0 + b0 (A-1)
@@ -199,13 +223,17 @@ static void enqueue_step(tts_ctx *c, const Launcher &L, int B) {
 static void ensure_rows(tts_ctx *c, size_t rows) {
   ArState &s = c->ars;
   if (rows <= s.rows_cap) return;
-  for (float **p : {&s.H, &s.A, &s.QKV, &s.ATT, &s.M})
-    if (*p) cudaFree(*p);
+  for (void *p : {(void *)s.H, (void *)s.QKV, (void *)s.Z, (void *)s.Ahi, (void *)s.Alo, (void *)s.ATThi,
+                  (void *)s.ATTlo, (void *)s.Mhi})
+    if (p) cudaFree(p);
   TTS_CUDA_TRY(cudaMalloc(&s.H, rows * kDim * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.A, rows * kDim * 4));
   TTS_CUDA_TRY(cudaMalloc(&s.QKV, rows * 3072 * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.ATT, rows * kDim * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.M, rows * kFF * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.Z, rows * kDim * 4));
+  TTS_CUDA_TRY(cudaMalloc(&s.Ahi, rows * kDim * 2));
+  TTS_CUDA_TRY(cudaMalloc(&s.Alo, rows * kDim * 2));
+  TTS_CUDA_TRY(cudaMalloc(&s.ATThi, rows * kDim * 2));
+  TTS_CUDA_TRY(cudaMalloc(&s.ATTlo, rows * kDim * 2));
+  TTS_CUDA_TRY(cudaMalloc(&s.Mhi, rows * kFF * 2));
   s.rows_cap = rows;
 }
 
@@ -218,18 +246,24 @@ static void enqueue_rows_layers(tts_ctx *c, const Launcher &L, int nb, int R, in
   const size_t layer_kv = size_t(s.Bmax) * kHeads * s.P * kHeadDim;
   for (int i = 0; i < kLayers; ++i) {
     ArLayer &l = m.layers[i];
-    L(ln_rows_kernel, dim3(rows), dim3(256), 0, (const float *)s.H, s.A, (const float *)l.ln1_w,
-      (const float *)l.ln1_b, (const float *)nullptr, (const float *)nullptr, kDim, kDim);
-    launch_sgemm(c, L, s.A, l.w_qkv, l.b_qkv, s.QKV, rows, 3072, kDim, kDim, 3072, E_BIAS_H16);
+    L(ln_rows_kernel, dim3(rows), dim3(256), 0, (const float *)s.H, (float *)nullptr, s.Ahi, s.Alo,
+      (const float *)l.ln1_w, (const float *)l.ln1_b, (const float *)nullptr, (const float *)nullptr, kDim, kDim);
+    launch_tgemm(c, L, s.Ahi, s.Alo, l.qkv_hi, l.qkv_lo, l.b_qkv, s.QKV, nullptr, nullptr, rows, 3072, kDim, kDim,
+                 3072, 0, E_BIAS_H16);
     if (kv_B > 0)
       L(ar_kv_scatter_kernel, dim3(R), dim3(256), 0, (const float *)s.QKV, s.kc + i * layer_kv,
         s.vc + i * layer_kv, R, kv_B, s.P);
-    L(ar_attn_causal_kernel, dim3((R + 15) / 16, kHeads, nb), dim3(128), 0, (const float *)s.QKV, s.ATT, R);
-    launch_sgemm(c, L, s.ATT, l.w_proj, l.b_proj, s.H, rows, kDim, kDim, kDim, kDim, E_BIAS_RESID);
-    L(ln_rows_kernel, dim3(rows), dim3(256), 0, (const float *)s.H, s.A, (const float *)l.ln2_w,
-      (const float *)l.ln2_b, (const float *)nullptr, (const float *)nullptr, kDim, kDim);
-    launch_sgemm(c, L, s.A, l.w_fc, l.b_fc, s.M, rows, kFF, kDim, kDim, kFF, E_BIAS_GELU16);
-    launch_sgemm(c, L, s.M, l.w_proj2, l.b_proj2, s.H, rows, kDim, kFF, kFF, kDim, E_BIAS_RESID);
+    L(ar_attn_causal_kernel, dim3((R + 15) / 16, kHeads, nb), dim3(128), 0, (const float *)s.QKV, s.ATThi,
+      s.ATTlo, R);
+    launch_tgemm(c, L, s.ATThi, s.ATTlo, l.proj_hi, l.proj_lo, l.b_proj, s.H, nullptr, nullptr, rows, kDim, kDim,
+                 kDim, kDim, 0, E_BIAS_RESID);
+    L(ln_rows_kernel, dim3(rows), dim3(256), 0, (const float *)s.H, (float *)nullptr, s.Ahi, s.Alo,
+      (const float *)l.ln2_w, (const float *)l.ln2_b, (const float *)nullptr, (const float *)nullptr, kDim, kDim);
+    // gelu16 outputs are f16-exact: a single plane carries them without loss
+    launch_tgemm(c, L, s.Ahi, s.Alo, l.fc_hi, l.fc_lo, l.b_fc, nullptr, s.Mhi, nullptr, rows, kFF, kDim, kDim, 0,
+                 kFF, E_BIAS_GELU16);
+    launch_tgemm(c, L, s.Mhi, nullptr, l.proj2_hi, l.proj2_lo, l.b_proj2, s.H, nullptr, nullptr, rows, kDim, kFF,
+                 kFF, kDim, 0, E_BIAS_RESID);
   }
 }
 
@@ -385,10 +419,10 @@ void ar_latents(tts_ctx *c, const int32_t *text, int T, const float *voice, cons
       (const float *)m.mel_pos, s.H);
     enqueue_rows_layers(c, L, nb, R, 0);
     // z = LN(LN(h) ln_f) lm_head.0  (main.cpp:2475-2499), all rows; mel rows are copied out
-    L(ln_rows_kernel, dim3(nb * R), dim3(256), 0, (const float *)s.H, s.A, (const float *)m.lnf_w,
-      (const float *)m.lnf_b, (const float *)m.lm0_w, (const float *)m.lm0_b, kDim, kDim);
+    L(ln_rows_kernel, dim3(nb * R), dim3(256), 0, (const float *)s.H, s.Z, (__half *)nullptr, (__half *)nullptr,
+      (const float *)m.lnf_w, (const float *)m.lnf_b, (const float *)m.lm0_w, (const float *)m.lm0_b, kDim, kDim);
     for (int b = 0; b < nb; ++b)
-      TTS_CUDA_TRY(cudaMemcpyAsync(out + size_t(b0 + b) * 500 * kDim, s.A + (size_t(b) * R + 1 + T) * kDim,
+      TTS_CUDA_TRY(cudaMemcpyAsync(out + size_t(b0 + b) * 500 * kDim, s.Z + (size_t(b) * R + 1 + T) * kDim,
                                    size_t(n_mel) * kDim * 4, cudaMemcpyDeviceToHost, c->stream));
     TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   }

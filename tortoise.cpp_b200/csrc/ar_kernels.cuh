@@ -5,7 +5,7 @@
 namespace tts {
 
 // h[b] = mel_emb[tok[b]] + mel_pos[pos_id]      (decode input, main.cpp:2668-2691)
-__global__ void __launch_bounds__(256) ar_embed_decode_kernel(const int *tokens, const int *state,
+static __global__ void __launch_bounds__(256) ar_embed_decode_kernel(const int *tokens, const int *state,
                                                               const float *mel_emb, const float *mel_pos,
                                                               float *h) {
   pdl_launch_dependents();
@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) ar_embed_decode_kernel(const int *tokens,
 //   rows 1..T        = text_emb[tok_j] + text_pos[j]
 //   rows T+1..       = mel_emb[code] + mel_pos[p]
 // codes/pos are per candidate ([B][n_mel]); text is shared.
-__global__ void __launch_bounds__(256) ar_embed_rows_kernel(const int *text, int T, const float *voice,
+static __global__ void __launch_bounds__(256) ar_embed_rows_kernel(const int *text, int T, const float *voice,
                                                             const int *codes, const int *mel_positions,
                                                             int n_mel, const float *text_emb,
                                                             const float *text_pos, const float *mel_emb,
@@ -51,9 +51,10 @@ __global__ void __launch_bounds__(256) ar_embed_rows_kernel(const int *text, int
 
 // y = LN(x) * w + b per row of 1024 (eps 1e-5, double accumulation, ggml.c:11905-11958);
 // optional second parameterised LN on top (the "double final norm", SURVEY A-1).
-__global__ void __launch_bounds__(256) ln_rows_kernel(const float *X, float *Y, const float *w1,
-                                                      const float *b1, const float *w2, const float *b2,
-                                                      int ldx, int ldy) {
+// Output: f32 Y (may be null) and/or split-f16 planes Yhi/Ylo (may be null) for tgemm.
+static __global__ void __launch_bounds__(256) ln_rows_kernel(const float *X, float *Y, __half *Yhi, __half *Ylo,
+                                                      const float *w1, const float *b1, const float *w2,
+                                                      const float *b2, int ldx, int ldy) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double red[8];
@@ -90,14 +91,24 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float *X, float *Y, 
     x[2] = d[2] * rstd * w4.z + b4.z;
     x[3] = d[3] * rstd * w4.w + b4.w;
   }
-  reinterpret_cast<float4 *>(Y + size_t(row) * ldy)[t] = make_float4(x[0], x[1], x[2], x[3]);
+  if (Y) reinterpret_cast<float4 *>(Y + size_t(row) * ldy)[t] = make_float4(x[0], x[1], x[2], x[3]);
+  if (Yhi) {
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      hi[i] = __float2half_rn(x[i]);
+      lo[i] = __float2half_rn(x[i] - __half2float(hi[i]));
+    }
+    *reinterpret_cast<uint2 *>(Yhi + size_t(row) * ldy + t * 4) = *reinterpret_cast<uint2 *>(hi);
+    if (Ylo) *reinterpret_cast<uint2 *>(Ylo + size_t(row) * ldy + t * 4) = *reinterpret_cast<uint2 *>(lo);
+  }
 }
 
 // Single-position attention against the f16 KV cache (main.cpp:2828-2886 with
 // test_dimension == 1): scores = q.k/8 over keys 0..n_past, softmax, weighted sum of v.
 // grid (16 heads, B), 128 threads.  K/V: [b][head][pos][64] f16 (the cached values ARE
 // f16-exact in the reference too: they pass through the F16 round trip, A-2).
-__global__ void __launch_bounds__(128) ar_attn_decode_kernel(const float *q, const __half *kc,
+static __global__ void __launch_bounds__(128) ar_attn_decode_kernel(const float *q, const __half *kc,
                                                              const __half *vc, float *out,
                                                              const int *state, int P) {
   extern __shared__ float sc[];  // [n] scores, then 2*64 partial outputs
@@ -159,7 +170,8 @@ __global__ void __launch_bounds__(128) ar_attn_decode_kernel(const float *q, con
 // 2828-2886 with n_past == 0).  QKV: [b][R][3072] f32 (already f16-rounded values).
 // grid (ceil(R/16), 16 heads, B), 128 threads = 4 warps, each warp 4 query rows.
 // Keys are staged through shared memory in tiles of 64; lane <-> key; online softmax.
-__global__ void __launch_bounds__(128) ar_attn_causal_kernel(const float *QKV, float *out, int R) {
+static __global__ void __launch_bounds__(128) ar_attn_causal_kernel(const float *QKV, __half *out_hi, __half *out_lo,
+                                                             int R) {
   constexpr int TK = 64, LDK = kHeadDim + 4;
   __shared__ __align__(16) float Ks[TK][LDK];
   __shared__ __align__(16) float Vs[TK][LDK];
@@ -253,16 +265,20 @@ __global__ void __launch_bounds__(128) ar_attn_causal_kernel(const float *QKV, f
     const int qi = q0 + warp * 4 + i;
     if (qi < R) {
       const float inv = 1.0f / l[i];
-      float *dst = out + (size_t(b) * R + qi) * kDim + head * kHeadDim;
-      dst[lane] = o[i][0] * inv;
-      dst[lane + 32] = o[i][1] * inv;
+      const size_t off = (size_t(b) * R + qi) * kDim + head * kHeadDim;
+      const float v0 = o[i][0] * inv, v1 = o[i][1] * inv;
+      const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+      out_hi[off + lane] = h0;
+      out_hi[off + lane + 32] = h1;
+      out_lo[off + lane] = __float2half_rn(v0 - __half2float(h0));
+      out_lo[off + lane + 32] = __float2half_rn(v1 - __half2float(h1));
     }
   }
 }
 
 // Copy K,V of the prefill rows into every candidate's f16 cache:
 // QKV [R][3072] (single shared sequence) -> kc/vc[b][head][pos][64] for b < B.
-__global__ void __launch_bounds__(256) ar_kv_scatter_kernel(const float *QKV, __half *kc, __half *vc, int R,
+static __global__ void __launch_bounds__(256) ar_kv_scatter_kernel(const float *QKV, __half *kc, __half *vc, int R,
                                                             int B, int P) {
   pdl_launch_dependents();
   pdl_wait();
@@ -280,7 +296,7 @@ __global__ void __launch_bounds__(256) ar_kv_scatter_kernel(const float *QKV, __
 }
 
 // dst[b][:] = src[:] for b < B (broadcast last prefill row to all candidates)
-__global__ void __launch_bounds__(256) bcast_row_kernel(const float *src, float *dst, int n) {
+static __global__ void __launch_bounds__(256) bcast_row_kernel(const float *src, float *dst, int n) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x;
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(256) bcast_row_kernel(const float *src, float 
 
 // transpose + convert at load time:  src f32 [K][N]  ->  dst WT [N][K]
 template <typename WT>
-__global__ void transpose_convert_kernel(const float *src, WT *dst, int K, int N) {
+static __global__ void transpose_convert_kernel(const float *src, WT *dst, int K, int N) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
@@ -305,8 +321,17 @@ __global__ void transpose_convert_kernel(const float *src, WT *dst, int K, int N
     }
   }
 }
+// src f32 [n] -> hi/lo f16 planes (parity-mode weights for the tensor-core row GEMMs)
+static __global__ void split_f16_kernel(const float *src, __half *hi, __half *lo, size_t n) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const float v = src[i];
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+}
 template <typename WT>
-__global__ void convert_kernel(const float *src, WT *dst, size_t n) {
+static __global__ void convert_kernel(const float *src, WT *dst, size_t n) {
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
     if constexpr (sizeof(WT) == 4) dst[i] = src[i];
     else dst[i] = __float2half_rn(src[i]);

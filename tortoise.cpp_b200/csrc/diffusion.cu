@@ -1,9 +1,406 @@
-// diffusion.cu -- placeholder until the diffusion stage lands.
-#include "common.cuh"
+// diffusion.cu -- diffusion stage: loader, conditioning pre-pass, denoiser pass, sampler.
+// Reference: diffusion_model_load (main.cpp:931-1634), diffusion_graph (main.cpp:3066-4044),
+// diffusion() (main.cpp:5614-6042).  B200-first restructuring (all exact w.r.t. the
+// reference's math): time-major f16 conv operands (implicit GEMM on tensor cores, no im2col),
+// conditioned + unconditioned passes batched as two sequences of one launch set, the
+// timestep-invariant conditioning branch hoisted out of the step loop, every timestep's
+// embedding MLP + the 16 emb_layers evaluated once per utterance as three GEMMs, the DDPM
+// update fused on the device (noise still drawn by the host in the reference's RNG order).
+#include <set>
+
+#include "diff_kernels.cuh"
 #include "engine.h"
+#include "gemm.cuh"
+#include "host/host_math.h"
+
 namespace tts {
-void diff_load(tts_ctx *, const char *) { throw ArgError("diffusion stage not built yet"); }
-void diff_eps(tts_ctx *, const float *, int, const float *, int, int, int, float *) { throw ArgError("diffusion stage not built yet"); }
-void diff_sample(tts_ctx *, const float *, int, int, int, const float *, float *) { throw ArgError("diffusion stage not built yet"); }
-void diff_free(tts_ctx *) {}
+
+struct DRes {
+  float *gn1_w, *gn1_b, *b_in2, *gn2_w, *gn2_b, *b_out3;
+  __half *w_in2, *w_out3;
+};
+struct DAttn {
+  float *n_w, *n_b, *b_qkv, *b_proj, *relbias;
+  __half *w_qkv, *proj_hi, *proj_lo;
+};
+struct DiffModel {
+  bool loaded = false;
+  DAttn lc[4];
+  __half *lc_conv_w;
+  float *lc_conv_b, *code_norm_w, *code_norm_b, *cond_latent, *uncond_emb;
+  __half *te0_hi, *te0_lo, *te2_hi, *te2_lo;
+  float *te0_b, *te2_b;
+  DRes res[16];    // 0-2 integrator, 3-12 main (with attention), 13-15 main tail
+  DAttn attn[13];  // 0-2 integrator, 3-12 main
+  __half *emb_hi, *emb_lo;  // [16*2048][1024] stacked emb_layers.1
+  float *emb_b;
+  __half *w_inp, *w_integ, *w_out;
+  float *b_inp, *b_integ, *b_out, *out_gn_w, *out_gn_b;
+  // work buffers
+  int capS = 0, capSteps = 0;
+  float *X = nullptr, *CW = nullptr, *CE = nullptr, *H1 = nullptr, *QKV = nullptr, *OUT = nullptr, *INP = nullptr;
+  float *stats = nullptr, *x_dev = nullptr, *noise_dev = nullptr, *lat_dev = nullptr;
+  __half *A16 = nullptr, *CAT16 = nullptr, *XIN16 = nullptr, *ATThi = nullptr, *ATTlo = nullptr;
+  int *rpb = nullptr, *up_idx = nullptr;
+  float *TE = nullptr, *T0 = nullptr, *TEMB = nullptr, *EMB = nullptr;
+  __half *P_hi = nullptr, *P_lo = nullptr;  // [steps][1024] planes scratch
+  DdpmCoef *coefs = nullptr;
+  float *h_pin = nullptr;  // pinned staging for x / outputs
+  size_t h_pin_bytes = 0;
+  // cached conditioning
+  int cond_L = -1, cond_S = -1;
+};
+
+static __half *upload_conv_w(tts_ctx *c, const Container &ct, const std::string &name, int OC, int IC, int K,
+                             int ICpad) {
+  auto it = ct.tensors.find(name);
+  if (it == ct.tensors.end()) throw ArgError("tensor '" + name + "' missing from " + ct.path, TTS_EIO);
+  if (it->second.nelem != size_t(OC) * IC * K) throw ArgError("tensor '" + name + "' has wrong size in model file", TTS_EIO);
+  // reference check (main.cpp:1585-1592): ne[0], ne[1] of the ggml shape [K, IC, OC] (2-D for 1x1)
+  const auto &ne = it->second.ne;
+  const int e0 = K > 1 ? K : IC, e1 = K > 1 ? IC : OC;
+  if (ne[0] != e0 || (ne.size() > 1 ? ne[1] : 1) != e1)
+    throw ArgError("tensor '" + name + "' has wrong shape in model file", TTS_EIO);
+  size_t n = 0;
+  read_tensor_to_staging(c, ct, name, &n);
+  __half *d = nullptr;
+  TTS_CUDA_TRY(cudaMalloc(&d, size_t(K) * OC * ICpad * 2));
+  conv_weight_kernel<<<1024, 256, 0, c->stream>>>(c->d_scratch, d, OC, IC, K, ICpad);
+  TTS_CUDA_TRY(cudaGetLastError());
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return d;
 }
+
+static void upload_planes(tts_ctx *c, const Container &ct, const std::string &name, int N, int K, __half *hi,
+                          __half *lo) {
+  auto it = ct.tensors.find(name);
+  if (it == ct.tensors.end()) throw ArgError("tensor '" + name + "' missing from " + ct.path, TTS_EIO);
+  const auto &ne = it->second.ne;
+  if (it->second.nelem != size_t(N) * K || ne[0] != K || (ne.size() > 1 ? ne[1] : 1) != N)
+    throw ArgError("tensor '" + name + "' has wrong shape in model file", TTS_EIO);
+  size_t n = 0;
+  read_tensor_to_staging(c, ct, name, &n);
+  silu_split_kernel<<<1024, 256, 0, c->stream>>>(c->d_scratch, hi, lo, n, 0);
+  TTS_CUDA_TRY(cudaGetLastError());
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+}
+
+void diff_load(tts_ctx *c, const char *path) {
+  Container ct;
+  std::string err;
+  if (!ct.open(path, err)) throw ArgError(err, TTS_EIO);
+  if (!c->diff) c->diff = new DiffModel();
+  DiffModel &m = *c->diff;
+  std::set<std::string> known;
+  auto f32 = [&](const std::string &n, std::vector<int> ne) { known.insert(n); return upload_f32(c, ct, n, ne); };
+  auto convw = [&](const std::string &n, int OC, int IC, int K, int ICpad) {
+    known.insert(n);
+    return upload_conv_w(c, ct, n, OC, IC, K, ICpad);
+  };
+  auto planes = [&](const std::string &n, int N, int K, __half **hi, __half **lo) {
+    known.insert(n);
+    TTS_CUDA_TRY(cudaMalloc(hi, size_t(N) * K * 2));
+    TTS_CUDA_TRY(cudaMalloc(lo, size_t(N) * K * 2));
+    upload_planes(c, ct, n, N, K, *hi, *lo);
+  };
+  auto load_attn = [&](const std::string &p, DAttn &a) {
+    a.n_w = f32(p + "norm.weight", {1024});
+    a.n_b = f32(p + "norm.bias", {1024});
+    a.w_qkv = convw(p + "qkv.weight", 3072, 1024, 1, 1024);
+    a.b_qkv = f32(p + "qkv.bias", {3072});
+    planes(p + "proj_out.weight", 1024, 1024, &a.proj_hi, &a.proj_lo);
+    a.b_proj = f32(p + "proj_out.bias", {1024});
+    a.relbias = f32(p + "relative_pos_embeddings.relative_attention_bias.weight", {16, 32});
+  };
+  TTS_CUDA_TRY(cudaMalloc(&m.emb_hi, size_t(16) * 2048 * 1024 * 2));
+  TTS_CUDA_TRY(cudaMalloc(&m.emb_lo, size_t(16) * 2048 * 1024 * 2));
+  TTS_CUDA_TRY(cudaMalloc(&m.emb_b, size_t(16) * 2048 * 4));
+  auto load_res = [&](const std::string &p, DRes &r, int idx) {
+    r.gn1_w = f32(p + "in_layers.0.weight", {1024});
+    r.gn1_b = f32(p + "in_layers.0.bias", {1024});
+    r.w_in2 = convw(p + "in_layers.2.weight", 1024, 1024, 1, 1024);
+    r.b_in2 = f32(p + "in_layers.2.bias", {1024});
+    known.insert(p + "emb_layers.1.weight");
+    upload_planes(c, ct, p + "emb_layers.1.weight", 2048, 1024, m.emb_hi + size_t(idx) * 2048 * 1024,
+                  m.emb_lo + size_t(idx) * 2048 * 1024);
+    float *eb = f32(p + "emb_layers.1.bias", {2048});
+    TTS_CUDA_TRY(cudaMemcpy(m.emb_b + size_t(idx) * 2048, eb, 2048 * 4, cudaMemcpyDeviceToDevice));
+    cudaFree(eb);
+    r.gn2_w = f32(p + "out_layers.0.weight", {1024});
+    r.gn2_b = f32(p + "out_layers.0.bias", {1024});
+    r.w_out3 = convw(p + "out_layers.3.weight", 1024, 1024, 3, 1024);
+    r.b_out3 = f32(p + "out_layers.3.bias", {1024});
+  };
+  m.cond_latent = f32("diffusion_conditioning_latent", {2048});
+  m.lc_conv_w = convw("latent_conditioner.0.weight", 1024, 1024, 3, 1024);
+  m.lc_conv_b = f32("latent_conditioner.0.bias", {1024});
+  for (int i = 0; i < 4; ++i) load_attn("latent_conditioner." + std::to_string(i + 1) + ".", m.lc[i]);
+  m.code_norm_w = f32("code_norm.weight", {1024});
+  m.code_norm_b = f32("code_norm.bias", {1024});
+  planes("time_embed.0.weight", 1024, 1024, &m.te0_hi, &m.te0_lo);
+  m.te0_b = f32("time_embed.0.bias", {1024});
+  planes("time_embed.2.weight", 1024, 1024, &m.te2_hi, &m.te2_lo);
+  m.te2_b = f32("time_embed.2.bias", {1024});
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = "conditioning_timestep_integrator." + std::to_string(i) + ".";
+    load_res(p + "resblk.", m.res[i], i);
+    load_attn(p + "attn.", m.attn[i]);
+  }
+  for (int i = 0; i < 10; ++i) {
+    const std::string p = "layers." + std::to_string(i) + ".";
+    load_res(p + "resblk.", m.res[3 + i], 3 + i);
+    load_attn(p + "attn.", m.attn[3 + i]);
+  }
+  for (int i = 0; i < 3; ++i) load_res("layers." + std::to_string(10 + i) + ".", m.res[13 + i], 13 + i);
+  m.w_inp = convw("inp_block.weight", 1024, 100, 3, 128);
+  m.b_inp = f32("inp_block.bias", {1024});
+  m.w_integ = convw("integrating_conv.weight", 1024, 2048, 1, 2048);
+  m.b_integ = f32("integrating_conv.bias", {1024});
+  m.out_gn_w = f32("out.0.weight", {1024});
+  m.out_gn_b = f32("out.0.bias", {1024});
+  m.w_out = convw("out.2.weight", 200, 1024, 3, 1024);
+  m.b_out = f32("out.2.bias", {200});
+  m.uncond_emb = f32("unconditioned_embedding", {1024});
+  for (const auto &n : ct.order)
+    if (!known.count(n)) throw ArgError("unknown tensor '" + n + "' in model file", TTS_EIO);
+  m.loaded = true;
+}
+
+void diff_free(tts_ctx *c) {
+  if (c->diff) {
+    if (c->diff->h_pin) cudaFreeHost(c->diff->h_pin);
+    delete c->diff;
+    c->diff = nullptr;
+  }
+}
+
+template <typename T>
+static void grow(T **p, size_t n) {
+  if (*p) cudaFree(*p);
+  TTS_CUDA_TRY(cudaMalloc(p, n * sizeof(T)));
+}
+
+static void ensure_buffers(tts_ctx *c, int S, int steps) {
+  DiffModel &m = *c->diff;
+  if (S > m.capS) {
+    const size_t s2 = size_t(2) * S;
+    grow(&m.X, s2 * kDim);
+    grow(&m.CW, s2 * kDim);
+    grow(&m.CE, s2 * kDim);
+    grow(&m.H1, s2 * kDim);
+    grow(&m.QKV, s2 * 3072);
+    grow(&m.OUT, s2 * 200);
+    grow(&m.INP, size_t(S) * kDim);
+    grow(&m.stats, size_t(2) * 32 * 2);
+    grow(&m.x_dev, size_t(100) * S);
+    grow(&m.lat_dev, size_t(S) * kDim);
+    grow(&m.A16, size_t(2) * (S + 2) * kDim);
+    grow(&m.CAT16, size_t(2) * (S + 2) * 2048);
+    grow(&m.XIN16, size_t(S + 2) * 128);
+    grow(&m.ATThi, s2 * kDim);
+    grow(&m.ATTlo, s2 * kDim);
+    grow(&m.rpb, size_t(S) + 8);
+    grow(&m.up_idx, size_t(S));
+    m.capS = S;
+    m.cond_L = m.cond_S = -1;
+  }
+  if (steps > m.capSteps) {
+    grow(&m.TE, size_t(steps) * kDim);
+    grow(&m.T0, size_t(steps) * kDim);
+    grow(&m.TEMB, size_t(steps) * kDim);
+    grow(&m.EMB, size_t(steps) * 16 * 2048);
+    grow(&m.P_hi, size_t(steps) * kDim);
+    grow(&m.P_lo, size_t(steps) * kDim);
+    grow(&m.coefs, size_t(steps));
+    m.capSteps = steps;
+  }
+}
+
+static void tg(tts_ctx *c, const Launcher &L, const __half *Ahi, const __half *Alo, const __half *Whi, const __half *Wlo,
+               const float *bias, float *C, int M, int N, int K, int lda, int ldc, int epi, int taps = 1, int T = 0,
+               int halo = 0) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    TTS_CUDA_TRY(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(tgemm_smem_bytes())));
+    attr_done = true;
+  }
+  TGemmArgs g{Ahi, Alo, Whi, Wlo, bias, C, nullptr, nullptr, M, N, K, lda, ldc, 0, epi, taps, 1, taps / 2, halo,
+              T > 0 ? T : M};
+  dim3 grid((N + TG_BN - 1) / TG_BN, (M + TG_BM - 1) / TG_BM);
+  L(tgemm_kernel, grid, dim3(128), tgemm_smem_bytes(), g);
+}
+
+// f16 x f16 -> f32 convolution over nseq sequences of T frames (halo 1)
+static void conv(tts_ctx *c, const Launcher &L, const __half *X16, const __half *W, const float *bias, float *C,
+                 int nseq, int T, int IC, int OC, int taps, int ldc, int epi) {
+  tg(c, L, X16, nullptr, W, nullptr, bias, C, nseq * T, OC, IC, IC, ldc, epi, taps, T, 1);
+}
+
+static void gn(tts_ctx *c, const Launcher &L, const float *X, const float *w, const float *b, const float *ss,
+               __half *out16, float *out32, int nseq, int T, int silu) {
+  DiffModel &m = *c->diff;
+  L(gn_stats_kernel, dim3(32, nseq), dim3(256), 0, X, m.stats, T);
+  L(gn_apply_kernel, dim3(T + 2, nseq), dim3(256), 0, X, (const float *)m.stats, w, b, ss, out16, out32, T, 1, kDim,
+    silu);
+}
+
+// ResBlock (main.cpp:3347-3480): x += conv3(silu((GN(h)w+b)(1+scale)+shift)),
+// h = conv1(silu(GN(x)w+b)) + b
+static void res_block(tts_ctx *c, const Launcher &L, const DRes &r, float *x, int nseq, int T, const float *ss) {
+  DiffModel &m = *c->diff;
+  gn(c, L, x, r.gn1_w, r.gn1_b, nullptr, m.A16, nullptr, nseq, T, 1);
+  conv(c, L, m.A16, r.w_in2, r.b_in2, m.H1, nseq, T, kDim, kDim, 1, kDim, E_BIAS);
+  gn(c, L, m.H1, r.gn2_w, r.gn2_b, ss, m.A16, nullptr, nseq, T, 1);
+  conv(c, L, m.A16, r.w_out3, r.b_out3, x, nseq, T, kDim, kDim, 3, kDim, E_BIAS_RESID);
+}
+
+// AttentionBlock (main.cpp:3482-3609): x += proj_out(attn(conv1(GN(x)w+b)))
+static void attn_block(tts_ctx *c, const Launcher &L, const DAttn &a, float *x, int nseq, int T) {
+  DiffModel &m = *c->diff;
+  gn(c, L, x, a.n_w, a.n_b, nullptr, m.A16, nullptr, nseq, T, 0);
+  conv(c, L, m.A16, a.w_qkv, a.b_qkv, m.QKV, nseq, T, kDim, 3072, 1, 3072, E_BIAS);
+  L(diff_attn_kernel, dim3((T + 15) / 16, kHeads, nseq), dim3(128), 0, (const float *)m.QKV,
+    (const float *)a.relbias, (const int *)m.rpb, m.ATThi, m.ATTlo, T);
+  tg(c, L, m.ATThi, m.ATTlo, a.proj_hi, a.proj_lo, a.b_proj, x, nseq * T, kDim, kDim, kDim, kDim, E_BIAS_RESID);
+}
+
+// timestep-invariant conditioning branch -> CE[0] (conditioned, stretched to S), CE[1]
+// (unconditioned broadcast).  main.cpp:3157-3328.
+static void prepare_conditioning(tts_ctx *c, const Launcher &L, const float *latents_host, int Lf, int S) {
+  DiffModel &m = *c->diff;
+  std::vector<int> rpb = tts_host::relative_position_table(S + 8);
+  std::vector<int> up = tts_host::upscale_index(Lf, S);
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.rpb, rpb.data(), size_t(S + 8) * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.up_idx, up.data(), size_t(S) * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.lat_dev, latents_host, size_t(Lf) * kDim * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+  L(to_f16_halo_kernel, dim3(Lf + 2), dim3(256), 0, (const float *)m.lat_dev, m.A16, Lf, kDim, 1, kDim);
+  conv(c, L, m.A16, m.lc_conv_w, m.lc_conv_b, m.CW, 1, Lf, kDim, kDim, 3, kDim, E_BIAS);
+  for (int i = 0; i < 4; ++i) attn_block(c, L, m.lc[i], m.CW, 1, Lf);
+  // code_norm, then * (1 + cond_latent[:1024]) + cond_latent[1024:]  (main.cpp:3293-3317)
+  gn(c, L, m.CW, m.code_norm_w, m.code_norm_b, m.cond_latent, nullptr, m.H1, 1, Lf, 0);
+  L(code_emb_kernel, dim3(S, 2), dim3(256), 0, (const float *)m.H1, (const int *)m.up_idx,
+    (const float *)m.uncond_emb, m.CE, S);
+  m.cond_L = Lf;
+  m.cond_S = S;
+}
+
+// time-embedding MLP + all 16 emb_layers for `steps` timesteps (main.cpp:3331-3343, 3418-3440)
+static void prepare_time(tts_ctx *c, const Launcher &L, const std::vector<int> &timesteps) {
+  DiffModel &m = *c->diff;
+  const int n = int(timesteps.size());
+  std::vector<float> te(size_t(n) * kDim);
+  for (int i = 0; i < n; ++i) tts_host::timestep_embedding(timesteps[i], te.data() + size_t(i) * kDim);
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.TE, te.data(), te.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const size_t ne = size_t(n) * kDim;
+  L(silu_split_kernel, dim3(64), dim3(256), 0, (const float *)m.TE, m.P_hi, m.P_lo, ne, 0);
+  tg(c, L, m.P_hi, m.P_lo, m.te0_hi, m.te0_lo, m.te0_b, m.T0, n, kDim, kDim, kDim, kDim, E_BIAS);
+  L(silu_split_kernel, dim3(64), dim3(256), 0, (const float *)m.T0, m.P_hi, m.P_lo, ne, 1);
+  tg(c, L, m.P_hi, m.P_lo, m.te2_hi, m.te2_lo, m.te2_b, m.TEMB, n, kDim, kDim, kDim, kDim, E_BIAS);
+  L(silu_split_kernel, dim3(64), dim3(256), 0, (const float *)m.TEMB, m.P_hi, m.P_lo, ne, 1);
+  tg(c, L, m.P_hi, m.P_lo, m.emb_hi, m.emb_lo, m.emb_b, m.EMB, n, 16 * 2048, kDim, kDim, 16 * 2048, E_BIAS);
+}
+
+// One denoiser evaluation on nseq sequences.  CW must hold the code embedding of each
+// sequence, x_dev the current x.  emb: this step's [16][2048] scale|shift table.
+static void run_denoiser(tts_ctx *c, const Launcher &L, int nseq, int S, const float *emb) {
+  DiffModel &m = *c->diff;
+  for (int i = 0; i < 3; ++i) {
+    res_block(c, L, m.res[i], m.CW, nseq, S, emb + size_t(i) * 2048);
+    attn_block(c, L, m.attn[i], m.CW, nseq, S);
+  }
+  L(xin_kernel, dim3(S + 2), dim3(128), 0, (const float *)m.x_dev, m.XIN16, S);
+  conv(c, L, m.XIN16, m.w_inp, m.b_inp, m.INP, 1, S, 128, kDim, 3, kDim, E_BIAS);
+  L(concat_kernel, dim3(S + 2, nseq), dim3(256), 0, (const float *)m.INP, (const float *)m.CW, m.CAT16, S);
+  conv(c, L, m.CAT16, m.w_integ, m.b_integ, m.X, nseq, S, 2048, kDim, 1, kDim, E_BIAS);
+  for (int i = 0; i < 10; ++i) {
+    res_block(c, L, m.res[3 + i], m.X, nseq, S, emb + size_t(3 + i) * 2048);
+    attn_block(c, L, m.attn[3 + i], m.X, nseq, S);
+  }
+  for (int i = 0; i < 3; ++i) res_block(c, L, m.res[13 + i], m.X, nseq, S, emb + size_t(13 + i) * 2048);
+  gn(c, L, m.X, m.out_gn_w, m.out_gn_b, nullptr, m.A16, nullptr, nseq, S, 1);
+  conv(c, L, m.A16, m.w_out, m.b_out, m.OUT, nseq, S, kDim, 200, 3, 200, E_BIAS);
+}
+
+static float *pin(tts_ctx *c, size_t bytes) {
+  DiffModel &m = *c->diff;
+  if (m.h_pin_bytes < bytes) {
+    if (m.h_pin) cudaFreeHost(m.h_pin);
+    TTS_CUDA_TRY(cudaMallocHost(&m.h_pin, bytes));
+    m.h_pin_bytes = bytes;
+  }
+  return m.h_pin;
+}
+
+static void check_sizes(tts_ctx *c, int Lf, int S) {
+  if (!c->diff || !c->diff->loaded) throw ArgError("diffusion model not loaded");
+  if (Lf < 1 || Lf > 500) throw ArgError("latent length must be in [1,500]", TTS_ELIMIT);
+  if (S < Lf || S > 4096) throw ArgError("bad mel length S", TTS_ELIMIT);
+}
+
+void diff_eps(tts_ctx *c, const float *latents, int Lf, const float *x, int S, int timestep, int cond_free,
+              float *out) {
+  check_sizes(c, Lf, S);
+  if (timestep < 0 || timestep >= 4000) throw ArgError("timestep out of range");
+  DiffModel &m = *c->diff;
+  ensure_buffers(c, S, 1);
+  Launcher L{c->stream, c->use_pdl, &c->launches};
+  TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  prepare_conditioning(c, L, latents, Lf, S);
+  prepare_time(c, L, {timestep});
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.x_dev, x, size_t(100) * S * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.CW, m.CE + (cond_free ? size_t(S) * kDim : 0), size_t(S) * kDim * 4,
+                               cudaMemcpyDeviceToDevice, c->stream));
+  run_denoiser(c, L, 1, S, m.EMB);
+  // OUT is time-major [S][200]; the C-ABI returns the reference's [200][S]
+  float *h = pin(c, size_t(S) * 200 * 4);
+  TTS_CUDA_TRY(cudaMemcpyAsync(h, m.OUT, size_t(S) * 200 * 4, cudaMemcpyDeviceToHost, c->stream));
+  TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  for (int t = 0; t < S; ++t)
+    for (int ch = 0; ch < 200; ++ch) out[size_t(ch) * S + t] = h[size_t(t) * 200 + ch];
+}
+
+void diff_sample(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, const float *noise, float *mel) {
+  check_sizes(c, Lf, S);
+  if (n_steps < 1 || n_steps > 4000) throw ArgError("bad n_steps");
+  DiffModel &m = *c->diff;
+  ensure_buffers(c, S, n_steps);
+  Launcher L{c->stream, c->use_pdl, &c->launches};
+  const size_t nx = size_t(100) * S;
+  TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  const std::vector<tts_host::DdpmStep> sched = tts_host::ddpm_schedule(n_steps);
+  std::vector<DdpmCoef> coefs(n_steps);
+  std::vector<int> timesteps(n_steps);
+  for (int i = 0; i < n_steps; ++i) {
+    const auto &s = sched[i];
+    coefs[i] = DdpmCoef{s.cfk, s.sqrt_recip, s.sqrt_recipm1, s.coef1, s.coef2, s.min_log, s.max_log, s.last};
+    timesteps[i] = s.timestep;
+  }
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.coefs, coefs.data(), coefs.size() * sizeof(DdpmCoef), cudaMemcpyHostToDevice, c->stream));
+  prepare_conditioning(c, L, latents, Lf, S);
+  prepare_time(c, L, timesteps);
+  // noise: block 0 = initial x, block i+1 = the draw of step i (always drawn, used unless last)
+  if (m.noise_dev) cudaFree(m.noise_dev);
+  m.noise_dev = nullptr;
+  TTS_CUDA_TRY(cudaMalloc(&m.noise_dev, size_t(n_steps + 1) * nx * 4));
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.noise_dev, noise, size_t(n_steps + 1) * nx * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.x_dev, m.noise_dev, nx * 4, cudaMemcpyDeviceToDevice, c->stream));
+  for (int i = 0; i < n_steps; ++i) {
+    TTS_CUDA_TRY(cudaMemcpyAsync(m.CW, m.CE, size_t(2) * S * kDim * 4, cudaMemcpyDeviceToDevice, c->stream));
+    run_denoiser(c, L, 2, S, m.EMB + size_t(i) * 16 * 2048);
+    L(ddpm_step_kernel, dim3(std::min(148, int((nx + 255) / 256))), dim3(256), 0, m.x_dev, (const float *)m.OUT,
+      (const float *)(m.noise_dev + size_t(i + 1) * nx), (const DdpmCoef *)m.coefs, i, S);
+  }
+  float *h = pin(c, nx * 4);
+  TTS_CUDA_TRY(cudaMemcpyAsync(h, m.x_dev, nx * 4, cudaMemcpyDeviceToHost, c->stream));
+  TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  memcpy(mel, h, nx * 4);
+}
+
+}  // namespace tts

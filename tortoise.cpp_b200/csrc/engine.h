@@ -30,6 +30,9 @@ struct ArLayer {
   float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
   void *w_qkv, *w_proj, *w_fc, *w_proj2;  // [N][K], f32 or f16
   float *b_qkv, *b_proj, *b_fc, *b_proj2;
+  // split-f16 planes for the tensor-core row GEMMs (prefill / latent pass).  Fast mode:
+  // hi aliases the f16 GEMV weights, lo is null.  Parity mode: hi/lo pair of the f32 weights.
+  __half *qkv_hi, *qkv_lo, *proj_hi, *proj_lo, *fc_hi, *fc_lo, *proj2_hi, *proj2_lo;
 };
 
 struct ArModel {
@@ -52,7 +55,8 @@ struct ArState {
   float *h_logits = nullptr;                    // pinned
   // row buffers for prefill / latent pass (grown on demand)
   size_t rows_cap = 0;
-  float *H = nullptr, *A = nullptr, *QKV = nullptr, *ATT = nullptr, *M = nullptr;
+  float *H = nullptr, *QKV = nullptr, *Z = nullptr;
+  __half *Ahi = nullptr, *Alo = nullptr, *ATThi = nullptr, *ATTlo = nullptr, *Mhi = nullptr;
   int *d_text = nullptr, *d_codes = nullptr, *d_pos = nullptr;
   float *d_voice = nullptr;
   // CUDA graph of one decode step, keyed by B

@@ -4,10 +4,12 @@
 //      Used where the reference multiplies in F32 (ggml_mul_mat with F32 operands): the AR
 //      prefill / latent pass (main.cpp:2053-2519), diffusion proj_out / emb_layers / time
 //      MLP (main.cpp:3331-3343, 3592-3596).
-//  (2) hgemm_conv_kernel (mma.sync m16n8k16, f16 x f16 -> f32): every ggml_conv_1d of the
-//      diffusion and vocoder graphs, whose reference numerics are F16 im2col x F16 weights
-//      with F32 accumulation (ggml.c:6493-6508, 15167-15248).  Implicit GEMM: K taps are
-//      K shifted GEMMs over a zero-padded, time-major activation buffer (no im2col).
+//  (2) tgemm_kernel (HMMA tensor cores, split-f16 operands, f32 accumulate): the F32 x F32
+//      matmuls of the AR prefill / latent pass and of diffusion (operands carried as hi/lo
+//      f16 planes), AND every ggml_conv_1d of the diffusion / vocoder graphs, whose reference
+//      numerics are F16 im2col x F16 weights with F32 accumulation (ggml.c:6493-6508,
+//      15167-15248) -- run as an implicit GEMM (taps = shifted K steps over a zero-haloed
+//      time-major activation buffer; no im2col buffer).
 #pragma once
 #include <mma.h>
 
@@ -22,6 +24,7 @@ enum Epi {
   E_BIAS_GELU16 = 3,  // gelu16(+bias)         (AR fc)
   E_BIAS_RESID = 4,   // C += acc + bias       (AR c_proj / mlp c_proj, diffusion proj_out)
   E_BIAS_LRELU = 5,   // leaky_relu(+bias, 0.2)
+  E_BIAS_LRELU_RESID = 6,  // C += leaky_relu(acc + bias, 0.2)   (vocoder kernel-predictor residual)
 };
 
 struct GemmArgs {
@@ -44,13 +47,17 @@ __device__ __forceinline__ float apply_epi(int epi, float acc, float bias, float
       const float v = acc + bias;
       return v > 0.f ? v : 0.2f * v;
     }
+    case E_BIAS_LRELU_RESID: {
+      const float v = acc + bias;
+      return old + (v > 0.f ? v : 0.2f * v);
+    }
   }
   return acc;
 }
 
 // ---- (1) SIMT f32 GEMM, 128x128x16 tiles, 256 threads, 8x8 micro-tiles -------------------
 template <typename WT>
-__global__ void __launch_bounds__(256) sgemm_tn_kernel(GemmArgs g) {
+static __global__ void __launch_bounds__(256) sgemm_tn_kernel(GemmArgs g) {
   constexpr int BM = 128, BN = 128, BK = 16;
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
@@ -137,129 +144,155 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(GemmArgs g) {
       if (n >= g.N) continue;
       float *c = g.C + size_t(m) * g.ldc + n;
       const float bias = g.bias ? g.bias[n] : 0.f;
-      const float old = g.epi == E_BIAS_RESID ? *c : 0.f;
+      const float old = (g.epi == E_BIAS_RESID || g.epi == E_BIAS_LRELU_RESID) ? *c : 0.f;
       *c = apply_epi(g.epi, acc[i][j], bias, old);
     }
   }
 }
 
-// ---- (2) f16 tensor-core implicit-GEMM 1-D convolution -------------------------------------
-// out[seq][t][oc] = epi( sum_{tap, ic} X[seq][t*stride_in? no: t + tap*dil - pad][ic] * W[tap][oc][ic] + bias[oc] )
-// Activations are TIME-MAJOR f16: X[seq][Tpad][IC] where each sequence carries `halo` zero
-// rows before and after its T valid rows (so taps never need predication); weights are
-// pre-converted once at load to f16 [taps][OC][IC] (reference casts them every graph run,
-// main.cpp:3163-3166).  Output is f32 [seq][T][ldo] (+ optional f16 copy for the next conv).
-struct ConvArgs {
-  const __half *X;     // [nseq][T + 2*halo][IC]
-  const __half *W;     // [taps][OC][IC]
-  const float *bias;   // [OC] or null
-  float *Y;            // [nseq][T][ldo]   f32 output (may be null)
-  __half *Yh;          // [nseq][T + 2*halo_o][ldoh] f16 output (may be null), written at row t+halo_o
-  const float *R;      // residual [nseq][T][ldo] added before store (may be null)
-  int nseq, T, IC, OC, taps, dil, pad, halo, ldo, halo_o, ldoh;
-  int epi;             // E_BIAS / E_BIAS_LRELU ...
+// ---- (1b) split-f16 tensor-core GEMM ---------------------------------------------------------
+// C[M][N] = (Ahi + Alo)[M][K] x (Whi + Wlo)[N][K]^T with f32 accumulation on the tensor cores:
+// an f32 operand x is carried as two f16 planes hi = f16(x), lo = f16(x - hi) (relative error
+// ~2^-22), so F32 x F32 reference matmuls (AR prefill / latent pass, diffusion proj_out) run on
+// tensor cores without changing their numerics beyond f32 rounding noise; operands that are
+// f16-exact in the reference (gelu16 outputs, f16 weights in fast mode) pass a null lo plane.
+// Products issued: Ahi.Whi (+ Alo.Whi) (+ Ahi.Wlo); the lo.lo term (2^-24) is dropped.
+// 64x64x32 CTA tile, 4 warps (2x2, 32x32 each), 3-stage cp.async pipeline.
+struct TGemmArgs {
+  const __half *Ahi, *Alo;  // [M][lda]; Alo may be null
+  const __half *Whi, *Wlo;  // [N][K];   Wlo may be null
+  const float *bias;        // [N] or null
+  float *C;                 // [M][ldc] f32 out (may be null); E_BIAS_RESID accumulates into it
+  __half *Chi, *Clo;        // [M][ldh] f16 planes of the result (may be null)
+  int M, N, K, lda, ldc, ldh;
+  int epi;
+  // implicit 1-D convolution (reference: ggml_conv_1d = F16 im2col x F16 kernel, F32 accumulate,
+  // ggml.c:6493-6508): taps > 1 turns the K loop into taps x (K/32) steps; A rows are addressed
+  // as time-major sequences [seq][T + 2*halo][lda] with zero halo rows, row m = seq*T + t reads
+  // A row seq*(T+2*halo) + t + halo + tap*dil - pad; W is [taps][N][K].  Plain GEMM: taps = 1,
+  // T = M, halo = pad = 0.
+  int taps, dil, pad, halo, T;
 };
 
-// 128 (time) x 128 (oc) x 32 (ic) CTA tile, 8 warps (4 x 2), warp tile 32 x 64.
-__global__ void __launch_bounds__(256) hconv_mma_kernel(ConvArgs c) {
+constexpr int TG_BM = 64, TG_BN = 64, TG_BK = 32, TG_LD = TG_BK + 8, TG_STAGES = 3;
+constexpr int TG_PLANE = TG_BM * TG_LD;  // halves per operand plane per stage
+__host__ __device__ inline size_t tgemm_smem_bytes() { return size_t(TG_STAGES) * 4 * TG_PLANE * sizeof(__half); }
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+static __global__ void __launch_bounds__(128) tgemm_kernel(TGemmArgs g) {
   using namespace nvcuda;
-  constexpr int BM = 128, BN = 128, BK = 32, LDS = BK + 8;
-  __shared__ __align__(32) __half As[2][BM][LDS];
-  __shared__ __align__(32) __half Bs[2][BN][LDS];
+  extern __shared__ __align__(128) unsigned char tg_smem[];
+  __half *sm = reinterpret_cast<__half *>(tg_smem);
   pdl_launch_dependents();
   pdl_wait();
-  const int tid = threadIdx.x, warp = tid / 32;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int wm = warp / 2, wn = warp % 2;
-  const int seq = blockIdx.z;
-  const int t0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int Tp = c.T + 2 * c.halo;
-  const __half *Xs = c.X + size_t(seq) * Tp * c.IC;
+  const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN;
+  const bool has_alo = g.Alo != nullptr, has_wlo = g.Wlo != nullptr;
 
-  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2][4];
+  auto plane = [&](int stage, int which) { return sm + (size_t(stage) * 4 + which) * TG_PLANE; };
+  // each thread moves 2 x 16 B per plane per stage: rows tid/4 and tid/4+32, chunk (tid%4)*8 halves
+  const int kchunks = g.K / TG_BK;
+  // A row base (in rows) of this thread's two tile rows, before the per-tap shift
+  long arow[2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int h = 0; h < 2; ++h) {
+    const int mc = min(m0 + tid / 4 + h * 32, g.M - 1);
+    const int seq = mc / g.T, t = mc % g.T;
+    arow[h] = long(seq) * (g.T + 2 * g.halo) + t + g.halo - g.pad;
+  }
+  auto load_stage = [&](int stage, int it) {
+    const int tap = it / kchunks, k0 = (it % kchunks) * TG_BK;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) wmma::fill_fragment(acc[i][j], 0.f);
-
-  const int kchunks = c.IC / BK;
-  const int iters = c.taps * kchunks;
-  // loader: 256 threads, each 16 halves (2 x uint4): row = tid/2, col = (tid%2)*16
-  const int lr = tid / 2, lc = (tid % 2) * 16;
-
-  auto load_tile = [&](int it, int buf) {
-    const int tap = it / kchunks, k0 = (it % kchunks) * BK;
-    {
-      const int t = t0 + lr;
-      uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
-      if (t < c.T) {
-        const int row = t + c.halo + tap * c.dil - c.pad;  // inside [0, Tp) by construction
-        const __half *p = Xs + size_t(row) * c.IC + k0 + lc;
-        u0 = *reinterpret_cast<const uint4 *>(p);
-        u1 = *reinterpret_cast<const uint4 *>(p + 8);
-      }
-      *reinterpret_cast<uint4 *>(&As[buf][lr][lc]) = u0;
-      *reinterpret_cast<uint4 *>(&As[buf][lr][lc + 8]) = u1;
-    }
-    {
-      const int n = n0 + lr;
-      uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
-      if (n < c.OC) {
-        const __half *p = c.W + (size_t(tap) * c.OC + n) * c.IC + k0 + lc;
-        u0 = *reinterpret_cast<const uint4 *>(p);
-        u1 = *reinterpret_cast<const uint4 *>(p + 8);
-      }
-      *reinterpret_cast<uint4 *>(&Bs[buf][lr][lc]) = u0;
-      *reinterpret_cast<uint4 *>(&Bs[buf][lr][lc + 8]) = u1;
+    for (int h = 0; h < 2; ++h) {
+      const int r = tid / 4 + h * 32, c = (tid % 4) * 8;
+      const int m = m0 + r, n = n0 + r;
+      const int nc = min(n, g.N - 1);
+      const int mb = m < g.M ? 16 : 0, nb = n < g.N ? 16 : 0;
+      const size_t aoff = size_t(arow[h] + tap * g.dil) * g.lda + k0 + c;
+      const size_t woff = (size_t(tap) * g.N + nc) * g.K + k0 + c;
+      cp_async16(plane(stage, 0) + r * TG_LD + c, g.Ahi + aoff, mb);
+      if (has_alo) cp_async16(plane(stage, 1) + r * TG_LD + c, g.Alo + aoff, mb);
+      cp_async16(plane(stage, 2) + r * TG_LD + c, g.Whi + woff, nb);
+      if (has_wlo) cp_async16(plane(stage, 3) + r * TG_LD + c, g.Wlo + woff, nb);
     }
   };
 
-  load_tile(0, 0);
-  __syncthreads();
-  for (int it = 0; it < iters; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < iters) load_tile(it + 1, buf ^ 1);
-#pragma unroll
-    for (int kk = 0; kk < BK; kk += 16) {
-      wmma::fragment<wmma::matrix_a, 16, 16, 16, __half, wmma::row_major> fa[2];
-      wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::col_major> fb[4];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) wmma::load_matrix_sync(fa[i], &As[buf][wm * 32 + i * 16][kk], LDS);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) wmma::load_matrix_sync(fb[j], &Bs[buf][wn * 64 + j * 16][kk], LDS);
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) wmma::mma_sync(acc[i][j], fa[i], fb[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-
-  // epilogue through shared memory (reuse As as f32 staging: 8 warps x 16x16 floats)
-  float *stage = reinterpret_cast<float *>(&As[0][0][0]) + warp * 256;
-  const int lane = tid % 32;
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      wmma::store_matrix_sync(stage, acc[i][j], 16, wmma::mem_row_major);
-      __syncwarp();
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int idx = e * 32 + lane;
-        const int r = idx / 16, cc = idx % 16;
-        const int t = t0 + wm * 32 + i * 16 + r;
-        const int n = n0 + wn * 64 + j * 16 + cc;
-        if (t < c.T && n < c.OC) {
-          float v = stage[idx] + (c.bias ? c.bias[n] : 0.f);
-          if (c.epi == E_BIAS_LRELU) v = v > 0.f ? v : 0.2f * v;
-          if (c.R) v += c.R[(size_t(seq) * c.T + t) * c.ldo + n];
-          if (c.Y) c.Y[(size_t(seq) * c.T + t) * c.ldo + n] = v;
-          if (c.Yh)
-            c.Yh[(size_t(seq) * (c.T + 2 * c.halo_o) + t + c.halo_o) * c.ldoh + n] = __float2half_rn(v);
-        }
-      }
-      __syncwarp();
+    for (int j = 0; j < 2; ++j) wmma::fill_fragment(acc[i][j], 0.f);
+
+  const int iters = g.taps * kchunks;
+  for (int s = 0; s < TG_STAGES - 1; ++s) {
+    if (s < iters) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int it = 0; it < iters; ++it) {
+    cp_async_wait<TG_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nx = it + TG_STAGES - 1;
+      if (nx < iters) load_stage(nx % TG_STAGES, nx);
+      cp_async_commit();
     }
+    const int st = it % TG_STAGES;
+#pragma unroll
+    for (int kk = 0; kk < TG_BK; kk += 16) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, __half, wmma::row_major> ah[2], al[2];
+      wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::col_major> wh[2], wl[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        wmma::load_matrix_sync(ah[i], plane(st, 0) + (wm * 32 + i * 16) * TG_LD + kk, TG_LD);
+        if (has_alo) wmma::load_matrix_sync(al[i], plane(st, 1) + (wm * 32 + i * 16) * TG_LD + kk, TG_LD);
+        wmma::load_matrix_sync(wh[i], plane(st, 2) + (wn * 32 + i * 16) * TG_LD + kk, TG_LD);
+        if (has_wlo) wmma::load_matrix_sync(wl[i], plane(st, 3) + (wn * 32 + i * 16) * TG_LD + kk, TG_LD);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (has_wlo) wmma::mma_sync(acc[i][j], ah[i], wl[j], acc[i][j]);
+          if (has_alo) wmma::mma_sync(acc[i][j], al[i], wh[j], acc[i][j]);
+          wmma::mma_sync(acc[i][j], ah[i], wh[j], acc[i][j]);
+        }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // epilogue: each warp stages its 32x32 f32 block in shared memory, then coalesced rows
+  float *stg = reinterpret_cast<float *>(tg_smem) + warp * (32 * 32);
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      wmma::store_matrix_sync(stg + (i * 16) * 32 + j * 16, acc[i][j], 32, wmma::mem_row_major);
+  __syncwarp();
+  const int n = n0 + wn * 32 + lane;
+  const float bias = (g.bias && n < g.N) ? g.bias[n] : 0.f;
+  for (int r = 0; r < 32; ++r) {
+    const int m = m0 + wm * 32 + r;
+    if (m >= g.M || n >= g.N) continue;
+    float old = 0.f;
+    if (g.epi == E_BIAS_RESID || g.epi == E_BIAS_LRELU_RESID) old = g.C[size_t(m) * g.ldc + n];
+    const float v = apply_epi(g.epi, stg[r * 32 + lane], bias, old);
+    if (g.C) g.C[size_t(m) * g.ldc + n] = v;
+    if (g.Chi) {
+      const __half hi = __float2half_rn(v);
+      g.Chi[size_t(m) * g.ldh + n] = hi;
+      if (g.Clo) g.Clo[size_t(m) * g.ldh + n] = __float2half_rn(v - __half2float(hi));
+    }
+  }
 }
 
 }  // namespace tts

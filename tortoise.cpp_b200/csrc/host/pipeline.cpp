@@ -1,0 +1,116 @@
+// pipeline.cpp -- the three stage drivers above the device C-ABI, mirroring the reference's
+// autoregressive() (main.cpp:5042-5367), diffusion() (5614-6042) and vocoder() (6044-6127):
+// same RNG draw order, same stop rule, same padding / trimming, same S = L*4*24000/22050.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/tortoise_b200.h"
+#include "../../../include/tortoise_host.h"
+#include "rng.h"
+
+namespace tts_host {
+int sample_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev, float *logprob);
+void apply_padding(std::vector<int32_t> &vec);
+int trim_count(const int32_t *codes500);
+}  // namespace tts_host
+
+extern "C" {
+
+int tts_host_autoregressive(struct tts_ctx *ctx, tts_rng *rng, const int32_t *tokens, int T, const float *voice,
+                            int B, const tts_ar_options *opt_in, int32_t *codes_out, float *latents_out,
+                            int32_t *n_latents, float *score_out, int32_t *steps_out) {
+  if (!ctx || !rng || !tokens || !voice || !codes_out || !latents_out || !n_latents || B < 1) return TTS_EINVAL;
+  tts_ar_options opt{};
+  if (opt_in) opt = *opt_in;
+  const int V = TTS_MEL_VOCAB, STOP = TTS_MEL_STOP;
+  std::vector<float> logits(size_t(B) * V);
+  int rc = tts_ar_prefill(ctx, tokens, T, voice, B, logits.data());
+  if (rc != TTS_OK) return rc;
+  // "mel_transformer_inputs_vector": [1]*(T+1) + [8192] per candidate (main.cpp:5095-5105)
+  int n_prev = T + 2;
+  std::vector<int32_t> prev(size_t(B) * n_prev, 1);
+  for (int b = 0; b < B; ++b) prev[size_t(b) * n_prev + n_prev - 1] = TTS_MEL_START;
+  std::vector<std::vector<int32_t>> seqs(B);
+  std::vector<int32_t> samples(B);
+  std::vector<double> lp_sum(B, 0.0);
+  std::vector<int> lp_n(B, 0);
+  std::vector<char> done(B, 0);
+  int i = 0;
+  for (;;) {
+    for (int b = 0; b < B; ++b) {
+      float *row = logits.data() + size_t(b) * V;
+      if (opt.forced_codes > 0 && i < opt.forced_codes) row[STOP] = -1e30f;  // bench mode: no early stop
+      float lp = 0.f;
+      samples[b] = tts_host::sample_one(rng->r, row, prev.data() + size_t(b) * n_prev, n_prev, &lp);
+      if (opt.forced_codes > 0 && i >= opt.forced_codes) samples[b] = STOP;
+      if (!done[b] && std::isfinite(lp)) {
+        lp_sum[b] += lp;
+        lp_n[b] += 1;
+      }
+    }
+    int stops = 0;
+    for (int b = 0; b < B; ++b) {
+      if (!(seqs[b].size() > 0 && seqs[b].back() == STOP)) seqs[b].push_back(samples[b]);
+      if (samples[b] == STOP) {
+        stops += 1;
+        done[b] = 1;
+      }
+    }
+    bool finished = stops == B;  // reference rule: all candidates emit 8193 in the SAME step
+    if (opt.per_candidate_stop) {
+      finished = true;
+      for (int b = 0; b < B; ++b) finished = finished && done[b];
+    }
+    prev.assign(samples.begin(), samples.end());
+    n_prev = 1;
+    if (finished) break;
+    for (int b = 0; b < B; ++b)
+      if (seqs[b].size() > 500) return TTS_ELIMIT;  // apply_padding asserts <= 500 (main.cpp:4517)
+    if (opt.max_steps > 0 && i + 1 >= opt.max_steps) return TTS_ELIMIT;
+    rc = tts_ar_step(ctx, samples.data(), i + 2, logits.data());  // fixed_position = i + 2 (main.cpp:5227)
+    if (rc != TTS_OK) return rc;
+    i += 1;
+  }
+  if (steps_out) *steps_out = i + 1;
+  std::vector<int32_t> codes502(size_t(B) * 502);
+  int n_keep = 1;
+  for (int b = 0; b < B; ++b) {
+    tts_host::apply_padding(seqs[b]);
+    if (seqs[b].size() != 502) return TTS_ELIMIT;
+    memcpy(codes502.data() + size_t(b) * 502, seqs[b].data(), 502 * 4);
+    memcpy(codes_out + size_t(b) * 500, seqs[b].data() + 1, 500 * 4);  // trim_latents drops first/last
+    n_latents[b] = tts_host::trim_count(codes_out + size_t(b) * 500);
+    if (n_latents[b] > n_keep) n_keep = n_latents[b];
+    if (score_out) score_out[b] = lp_n[b] ? float(lp_sum[b] / lp_n[b]) : 0.f;
+  }
+  rc = tts_ar_latents(ctx, tokens, T, voice, codes502.data(), B, n_keep, latents_out);
+  if (rc != TTS_OK) return rc;
+  for (int b = 0; b < B; ++b)  // zero the rows trim_latents would not return
+    memset(latents_out + (size_t(b) * 500 + n_latents[b]) * 1024, 0, size_t(500 - n_latents[b]) * 1024 * 4);
+  return TTS_OK;
+}
+
+int tts_host_diffusion(struct tts_ctx *ctx, tts_rng *rng, const float *latents, int L, int n_steps, float *mel_out,
+                       int32_t *S_out) {
+  if (!ctx || !rng || !latents || !mel_out || L < 1 || n_steps < 1) return TTS_EINVAL;
+  const int S = L * 4 * 24000 / 22050;  // main.cpp:5616-5617 (integer arithmetic)
+  if (S_out) *S_out = S;
+  const size_t nx = size_t(100) * S;
+  // RNG order: initial x (main.cpp:5638), then one block per step (main.cpp:6020), drawn every
+  // step including the last.  Nothing else consumes the generator in between, so drawing the
+  // blocks up front is the same stream.
+  std::vector<float> noise((size_t(n_steps) + 1) * nx);
+  for (size_t i = 0; i < noise.size(); ++i) noise[i] = rng->r.normal(rng->r.generator);
+  return tts_diffusion_sample(ctx, latents, L, S, n_steps, noise.data(), mel_out);
+}
+
+int tts_host_vocoder(struct tts_ctx *ctx, tts_rng *rng, const float *mel, int S, float *audio_out) {
+  if (!ctx || !rng || !mel || !audio_out || S < 1) return TTS_EINVAL;
+  std::vector<float> noise(size_t(S + 10) * 64);  // main.cpp:6057
+  for (size_t i = 0; i < noise.size(); ++i) noise[i] = rng->r.normal(rng->r.generator);
+  return tts_vocoder(ctx, mel, S, noise.data(), audio_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// sampler.cpp -- RNG + logits post-processing + sampling, padding and trimming: the host
+// logic of the AR stage (main.cpp:4510-4532, 4562-4720, 4753-4806, 4873-4915).
+//
+// Two implementations of process_logits_and_sample:
+//  * sample_literal(): the reference's algorithm step for step (full sorts of 8194 floats);
+//  * sample_fast(): same results in O(V + k log k).  Only the >= 50 logits that survive top-k
+//    can have non-zero probability, exp(lowest()) == 0 exactly, and adding 0.0f is exact, so
+//    every float sum the reference forms over 8194 entries equals the same sum over the
+//    survivors in the same order.  If two survivors tie (the only case where std::sort's
+//    unspecified order of equal keys could matter) it defers to sample_literal().
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <random>
+#include <vector>
+
+#include "rng.h"
+
+namespace tts_host {
+
+constexpr int V = 8194;
+
+static int multinomial(Rng &r, const float *probs, int n) {
+  float sample = r.distribution(r.generator);
+  sample = r.distribution(r.generator);  // two draws, second used (main.cpp:4708-4709)
+  float cum = 0;
+  for (int i = 0; i < n; ++i) {
+    cum += probs[i];
+    if (cum >= sample) return i;
+  }
+  return V - 1;
+}
+
+static void penalise(std::vector<float> &lg, const int32_t *prev, int n_prev) {
+  // gather -> apply_penalty(2.0) -> scatter (main.cpp:4770-4775): every scatter writes a value
+  // derived from the ORIGINAL logit, so duplicates in prev are idempotent.
+  std::vector<float> orig(n_prev);
+  for (int i = 0; i < n_prev; ++i) orig[i] = lg[prev[i]];
+  for (int i = 0; i < n_prev; ++i) lg[prev[i]] = orig[i] < 0 ? orig[i] * 2.0f : orig[i] / 2.0f;
+}
+
+int sample_literal_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev) {
+  std::vector<float> lg(logits_row, logits_row + V);
+  penalise(lg, prev, n_prev);
+  const float temp = 0.8;
+  for (float &x : lg) x /= temp;
+  {  // top_k_inplace(50)
+    std::vector<float> s(lg);
+    std::sort(s.begin(), s.end());
+    const float kth = s[s.size() - 50];
+    for (float &x : lg)
+      if (x < kth) x = std::numeric_limits<float>::lowest();
+  }
+  {  // top_p_inplace
+    std::vector<std::pair<float, int>> pairs;
+    for (int i = 0; i < V; ++i) pairs.push_back(std::make_pair(lg[i], i));
+    std::sort(pairs.begin(), pairs.end(),
+              [](const std::pair<float, int> &a, const std::pair<float, int> &b) { return a.first < b.first; });
+    std::vector<float> sl(V);
+    float sum = 0;
+    for (int i = 0; i < V; ++i) {
+      sl[i] = std::exp(pairs[i].first);
+      sum += sl[i];
+    }
+    for (int i = 0; i < V; ++i) sl[i] /= sum;
+    for (int i = 1; i < V; ++i) sl[i] += sl[i - 1];
+    for (int i = 0; i < V - 1; ++i)
+      if (sl[i] <= 0.2) lg[pairs[i].second] = std::numeric_limits<float>::lowest();
+  }
+  float sum = 0;
+  for (float &x : lg) {
+    x = std::exp(x);
+    sum += x;
+  }
+  for (float &x : lg) x /= sum;
+  return multinomial(r, lg.data(), V);
+}
+
+// returns -1 when it must defer to the literal path (ties among survivors)
+static int sample_fast_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev, float *logprob) {
+  std::vector<float> lg(logits_row, logits_row + V);
+  penalise(lg, prev, n_prev);
+  const float temp = 0.8;
+  for (float &x : lg) x /= temp;
+  std::vector<float> s(lg);
+  std::nth_element(s.begin(), s.begin() + (V - 50), s.end());
+  const float kth = s[V - 50];
+  std::vector<std::pair<float, int>> surv;  // (value, index), in index order
+  for (int i = 0; i < V; ++i)
+    if (!(lg[i] < kth)) surv.push_back(std::make_pair(lg[i], i));
+  std::vector<std::pair<float, int>> asc(surv);
+  std::sort(asc.begin(), asc.end());  // by value, then index
+  for (size_t i = 1; i < asc.size(); ++i)
+    if (asc[i].first == asc[i - 1].first) return -1;
+  if ((int)surv.size() == V) return -1;  // degenerate: nothing was cut
+  // top-p over the ascending survivors; the V - |surv| masked entries contribute exact zeros
+  // and sort before every survivor, so index i of the full sorted array = i - n_masked here.
+  const int ns = int(asc.size());
+  std::vector<float> e(ns);
+  float sum = 0;
+  for (int i = 0; i < ns; ++i) {
+    e[i] = std::exp(asc[i].first);
+    sum += e[i];
+  }
+  std::vector<char> dead(V, 0);
+  float cum = 0;
+  for (int i = 0; i < ns; ++i) {
+    const float p = e[i] / sum;
+    cum = (i == 0) ? p : cum + p;  // masked prefix sums to exactly 0.0f
+    if (i < ns - 1 && cum <= 0.2) dead[asc[i].second] = 1;  // the last (largest) entry is never cut
+  }
+  // final softmax + multinomial in index order over what is left
+  std::vector<std::pair<float, int>> fin;
+  float fsum = 0;
+  for (const auto &pr : surv)
+    if (!dead[pr.second]) {
+      const float ex = std::exp(pr.first);
+      fin.push_back(std::make_pair(ex, pr.second));
+      fsum += ex;
+    }
+  float sample = r.distribution(r.generator);
+  sample = r.distribution(r.generator);
+  int pick = V - 1;
+  float pickp = 0.f;
+  if (!(0.0f < sample)) {
+    pick = 0;  // cumulative 0 >= sample already holds at index 0 (main.cpp:4713-4716)
+    pickp = (!fin.empty() && fin[0].second == 0) ? fin[0].first / fsum : 0.f;
+  } else {
+    float c = 0;
+    bool found = false;
+    for (const auto &pr : fin) {
+      const float p = pr.first / fsum;
+      c += p;
+      if (c >= sample) {
+        pick = pr.second;
+        pickp = p;
+        found = true;
+        break;
+      }
+    }
+    if (!found) {
+      pick = V - 1;
+      pickp = 0.f;
+      for (const auto &pr : fin)
+        if (pr.second == V - 1) pickp = pr.first / fsum;
+    }
+  }
+  if (logprob) *logprob = pickp > 0.f ? std::log(pickp) : -std::numeric_limits<float>::infinity();
+  return pick;
+}
+
+int sample_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev, float *logprob) {
+  const Rng saved = r;
+  const int s = sample_fast_one(r, logits_row, prev, n_prev, logprob);
+  if (s >= 0) return s;
+  r = saved;  // fast path consumed nothing before deciding, but stay safe
+  if (logprob) *logprob = 0.f;
+  return sample_literal_one(r, logits_row, prev, n_prev);
+}
+
+void apply_padding(std::vector<int32_t> &vec) {  // main.cpp:4510-4532
+  while (!vec.empty() && vec.back() == 8139) vec.pop_back();  // sic: 8139, not 8193
+  for (size_t i = vec.size(); i < 500; ++i) vec.push_back(83);
+  vec[vec.size() - 3] = 45;
+  vec[vec.size() - 2] = 45;
+  vec[vec.size() - 1] = 248;
+  vec.push_back(8193);
+  vec.insert(vec.begin(), 8192);
+}
+
+int trim_count(const int32_t *codes500) {  // main.cpp:4894-4911
+  int calm = 0;
+  for (int c = 0; c < 500; ++c) {
+    calm = codes500[c] == 83 ? calm + 1 : 0;
+    if (calm > 8) return c;
+  }
+  return 500;
+}
+
+}  // namespace tts_host
