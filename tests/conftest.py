@@ -58,6 +58,8 @@ def has_gpu():
 def engine_f32(pkg, model_dir):
     eng = pkg.Engine(device=0, dtype=pkg.DTYPE_F32, max_batch=4, max_positions=404, parity_quirks=True)
     eng.load_ar(os.path.join(model_dir, "ggml-model.bin"))
+    eng.load_diffusion(os.path.join(model_dir, "ggml-diffusion-model.bin"))
+    eng.load_vocoder(os.path.join(model_dir, "ggml-vocoder-model.bin"))
     yield eng
     eng.close()
 
@@ -65,3 +67,17 @@ def engine_f32(pkg, model_dir):
 @pytest.fixture(scope="session")
 def voice():
     return np.fromfile(os.path.join(GOLDEN, "models", "mol.bin"), dtype=np.float32)
+
+
+@pytest.fixture(scope="session")
+def hostlib_full():
+    import _pkg
+    return _pkg.import_sub("host").HostLib(full=True)
+
+
+def nmse(a, b):
+    """normalised mean squared error, the metric of ggml's own cross-backend test
+    (ggml/tests/test-backend-ops.cpp:193-206)."""
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    return float(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-30))

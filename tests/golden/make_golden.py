@@ -110,7 +110,7 @@ def main():
          "trimmed_latents": f32(W + "/out_full/trimmed_latents_0.f32")}
     logit_files = sorted(glob.glob(W + "/out_full/ar_get*_c*.f32"))
     logit_files = [p for p in logit_files if os.path.getsize(p) == 8194 * 4]
-    keep = sorted({0, 1, 2, len(logit_files) // 2, len(logit_files) - 1})
+    keep = range(len(logit_files))  # every step: the free-running comparison needs them all
     for k in keep:
         d[f"logits_{k}"] = f32(logit_files[k])
     d["n_logit_steps"] = np.array(len(logit_files))

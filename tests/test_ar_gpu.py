@@ -37,6 +37,7 @@ def test_prefill_and_teacher_forced_decode_b1(engine_f32, golden, voice):
     assert np.abs(lg[0] - g["logits_0"]).max() < LOGIT_TOL
     toks = _codes_to_steps(g["codes500"])
     steps = {int(k.split("_")[1]) for k in g.files if k.startswith("logits_")}
+    assert steps == set(range(len(toks) + 1))  # every decode step of the reference run is pinned
     for i, t in enumerate(toks):
         lg = engine_f32.ar_step([t], i + 2)  # reference: fixed_position = i + 2 (main.cpp:5227)
         if (i + 1) in steps:
@@ -136,8 +137,6 @@ def test_fp16_weight_mode_tracks_oracle(pkg, golden, voice, model_dir):
         ref = ar.step(np.array(toks), 2)
         lg = eng.ar_step(toks, 2)
         assert np.abs(lg - ref).max() < LOGIT_TOL
-        # f16 weights stay close to the f32 reference too (weight rounding only)
-        assert np.abs(lg[0] - g["logits_1"]).max() < 0.05 or True
     finally:
         eng.close()
 
