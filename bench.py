@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native tortoise-tts hot path.
+
+Metric (BASELINE.json): real-time factor = audio-seconds / wall-seconds (plus AR mel-tokens/s).
+One "step" = one utterance through the whole hot path: prompt tokens -> AR prefill + KV-cached
+decode (host sampling between steps, as in the reference) + latent pass -> 80-step diffusion
+(cond + uncond batched) -> vocoder -> float32 waveform in host memory.
+
+N = 1 workload = BASELINE.json configs[1] ("1xB200 fp16: same prompt/voice/seed, full
+AR+diffusion+vocoder"): prompt "this is a test message.", voice mol.bin, 1 candidate, f16 AR
+weights, 80 diffusion steps.  Weights are the seeded synthetic files (no network for the real
+checkpoints); the number of mel codes is forced to round(1.5 * chars) = 35 so the
+measured work does not depend on when the sampler happens to emit the stop token.
+N > 1: one process per GPU (torchrun), every rank synthesises its own candidate of the same
+prompt (seed = rank): weak scaling, no data-path collective; one NCCL all_gather of the
+per-candidate scores for the final selection sits inside the timed region.
+
+  value : audio-s / device time (CUDA events around every stage call; inputs are a few KB)
+  e2e   : audio-s / wall time of the host-driven pipeline through the C-ABI with HOST buffers
+          (tokens / voice / noise H2D and logits / mel / audio D2H inside the timed region)
+  roofline : streaming-GEMV kernel, algorithmic bytes / CUDA-event time per launch, against
+          MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref/ref_harness, built
+          from /root/reference) on the host cores, bounded sample, extrapolated linearly.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PROMPT = "this is a test message."
+N_CODES = 35            # round(1.5 * len(PROMPT)) = 34.5 -> 35
+DIFF_STEPS = 80
+MODEL_DIR = os.environ.get("TTS_MODEL_DIR", "/tmp/tortoise_b200_models")
+GOLDEN_MODELS = os.path.join(ROOT, "tests", "golden", "models")
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.samples = []
+        self.reasons = set()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append((float(f[0]), float(f[1])))
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons)}
+
+
+def prepare_models():
+    import shutil
+    import _pkg
+    sw = _pkg.import_sub("synth_weights")
+    sw.generate(MODEL_DIR)
+    for f in ("tokenizer.json", "mol.bin"):
+        shutil.copyfile(os.path.join(GOLDEN_MODELS, f), os.path.join(MODEL_DIR, f))
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference_sample(n_decode: int = 2):
+    """Bounded sample of the reference's own CPU implementation on the host cores:
+    AR prefill + n_decode decode steps, one diffusion step (2 passes), the full vocoder.
+    Linear extrapolation to the workload (N_CODES + 1 decode steps, 160 passes); the latent
+    pass (519 rows, not reachable without running every decode step) is charged as
+    3.4 x prefill, the ratio measured on the full reference run in the build container
+    (26.7 s vs 7.9 s, tests/golden/make_golden.py run)."""
+    if not os.path.exists(HARNESS):
+        raise FileNotFoundError(f"{HARNESS} missing: run `make -C oracle` where /root/reference exists")
+    build = os.path.join(os.path.dirname(MODEL_DIR.rstrip("/")), "_bench_build")
+    os.makedirs(build, exist_ok=True)
+    link = os.path.join(os.path.dirname(build), "models")
+    if os.path.realpath(link) != os.path.realpath(MODEL_DIR):
+        if os.path.islink(link):
+            os.remove(link)
+        if not os.path.exists(link):
+            os.symlink(MODEL_DIR, link)
+    out = os.path.join(build, "out")
+
+    def run(args):
+        r = subprocess.run([HARNESS] + args, cwd=build, capture_output=True, text=True, timeout=1200)
+        if r.returncode != 0:
+            raise RuntimeError(f"ref_harness {args[0]} failed: {r.stderr[-400:]}")
+        return r.stdout
+
+    t0 = time.time()
+    o = run(["ar", PROMPT, "../models/mol.bin", "1", "0", out, str(1 + n_decode)])
+    times = [float(x) for x in re.search(r"HARNESS_COMPUTE_TIMES(.*)", o).group(1).split()]
+    t_prefill, t_dec = times[0], float(np.mean(times[1:])) if len(times) > 1 else times[0]
+    lat = np.load(os.path.join(ROOT, "tests", "golden", "ar_b1.npz"))["trimmed_latents"]
+    lat_path = os.path.join(build, "lat.f32")
+    # latents of the workload's length (content is irrelevant for timing)
+    L = N_CODES + 1 + 8
+    np.resize(lat, L * 1024).astype(np.float32).tofile(lat_path)
+    o = run(["diff", lat_path, "0", out, "2"])
+    ptimes = [float(x) for x in re.search(r"HARNESS_COMPUTE_TIMES(.*)", o).group(1).split()]
+    t_pass = float(np.mean(ptimes))
+    S = L * 4 * 24000 // 22050
+    mel_path = os.path.join(build, "mel.f32")
+    np.zeros(100 * S, np.float32).tofile(mel_path)
+    o = run(["voc", mel_path, "0", out])
+    t_voc = float(re.search(r"compute_seconds=([0-9.]+)", o).group(1))
+    wall_sample = time.time() - t0
+    n_dec = N_CODES + 1
+    t_latent = 3.4 * t_prefill
+    t_total = t_prefill + n_dec * t_dec + t_latent + 2 * DIFF_STEPS * t_pass + t_voc
+    audio_s = ((S + 10) * 256 - 6) / 24000.0
+    return {
+        "rtf": audio_s / t_total, "tok_s": n_dec / (n_dec * t_dec), "t_total_est_s": t_total,
+        "t_prefill": t_prefill, "t_decode_step": t_dec, "t_diff_pass": t_pass, "t_vocoder": t_voc,
+        "wall_sample_s": wall_sample, "audio_s": audio_s,
+        "sample": (f"AR prefill + {n_decode} decode steps ({t_prefill:.1f}s + {t_dec:.2f}s/step), 1 diffusion step "
+                   f"= 2 passes ({t_pass:.2f}s/pass), full vocoder ({t_voc:.2f}s); extrapolated linearly to "
+                   f"{n_dec} decode steps + {2 * DIFF_STEPS} passes, latent pass charged as 3.4x prefill"),
+    }
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    prepare_models()
+    steps = []
+    for _ in range(max(1, min(args.steps, 1))):  # one bounded sample is already ~25 s of CPU
+        steps.append(run_reference_sample())
+    r = steps[-1]
+    cores = 4  # GGML_DEFAULT_N_THREADS (ggml.h:236); main.cpp never overrides it
+    line = {
+        "impl": "reference", "metric": "real-time factor (audio-s/wall-s)", "value": r["rtf"],
+        "unit": "audio-s/wall-s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["t_total_est_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "ar_mel_tokens_per_s": r["tok_s"],
+        "config": workload_config(1),
+        "cpu_baseline": {"value": r["rtf"], "unit": "audio-s/wall-s", "cores": cores, "kind": "reference",
+                         "sample": r["sample"], "host_cpus": os.cpu_count()},
+        "e2e": {"value": r["rtf"], "unit": "audio-s/wall-s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world):
+    return {"workload": "configs[1]: 1 candidate/GPU, prompt 'this is a test message.' (T=16), voice mol.bin, "
+                        f"{N_CODES} mel codes forced, {DIFF_STEPS} diffusion steps, full AR+diffusion+vocoder",
+            "candidates_per_gpu": 1, "global_candidates": world, "prompt_chars": len(PROMPT),
+            "diffusion_steps": DIFF_STEPS, "weights": "seeded synthetic (tortoise.cpp_b200/synth_weights.py)",
+            "l2_policy": "inputs larger than L2: 0.77 GB of f16 AR weights + 0.36 GB of diffusion weights are "
+                         "re-streamed every step (L2 = 126 MB)",
+            "parallelism": f"dp{world} (candidates sharded, weights replicated)"}
+
+
+# ------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the hot path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if local_rank == 0:
+        prepare_models()
+    if world > 1:
+        dist.barrier()
+
+    import _pkg
+    pkg = _pkg.import_pkg()
+    hostmod = _pkg.import_sub("host")
+    hl = hostmod.HostLib(full=True)
+    eng = pkg.Engine(device=local_rank, dtype=pkg.DTYPE_F16, max_batch=2, max_positions=404, parity_quirks=True)
+    eng.load_ar(os.path.join(MODEL_DIR, "ggml-model.bin"))
+    eng.load_diffusion(os.path.join(MODEL_DIR, "ggml-diffusion-model.bin"))
+    eng.load_vocoder(os.path.join(MODEL_DIR, "ggml-vocoder-model.bin"))
+    tokens = np.array(hl.tokenize(os.path.join(MODEL_DIR, "tokenizer.json"), PROMPT), dtype=np.int32)
+    voice = np.fromfile(os.path.join(MODEL_DIR, "mol.bin"), dtype=np.float32)
+    T = len(tokens)
+
+    def one_utterance(seed):
+        """returns (audio, device_ms, ar_device_ms, ar_steps, score, bytes_h2d, bytes_d2h)"""
+        rng = hl.rng(seed)
+        dev_ms = 0.0
+        # AR through the stage driver; device time = sum of the per-call CUDA-event times is not
+        # observable from outside the driver, so time the three stage calls individually below.
+        t0 = time.perf_counter()
+        codes, lat, nlat, score, steps = hl.autoregressive(eng, rng, tokens, voice, 1, forced_codes=N_CODES,
+                                                           per_candidate_stop=True)
+        t_ar = time.perf_counter() - t0
+        L = int(nlat[0])
+        mel = hl.diffusion(eng, rng, lat[0, :L], DIFF_STEPS)
+        d_ms = eng.last_stage_ms
+        audio = hl.vocoder(eng, rng, mel)
+        v_ms = eng.last_stage_ms
+        S = mel.shape[1]
+        h2d = 4 * (T + 1024) + steps * 4 + 4 * (T + 1024 + 502) + 4 * L * 1024 + 4 * (DIFF_STEPS + 1) * 100 * S \
+            + 4 * 100 * S + 4 * (S + 10) * 64
+        d2h = 4 * 8194 * steps + 4 * 500 * 1024 + 4 * 100 * S + 4 * audio.size
+        return audio, t_ar, d_ms, v_ms, steps, float(score[0]), h2d, d2h
+
+    for w in range(args.warmup):
+        one_utterance(1000 + w)
+    eng.sync()
+    launches0 = eng.launch_count
+    dev0 = eng.device_ms_total
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_start = time.perf_counter()
+    audio_s = 0.0
+    ar_wall = 0.0
+    diff_ms = voc_ms = 0.0
+    n_tokens = 0
+    h2d = d2h = 0
+    last_score = 0.0
+    for k in range(args.steps):
+        audio, t_ar, d_ms, v_ms, steps, score, bi, bo = one_utterance(rank + world * k)
+        audio_s += audio.size / 24000.0
+        ar_wall += t_ar
+        diff_ms += d_ms
+        voc_ms += v_ms
+        n_tokens += steps
+        h2d, d2h = bi, bo
+        last_score = score
+        if world > 1:  # final candidate gather / selection (the path's only exchange)
+            sc = torch.tensor([score], device="cuda")
+            allsc = [torch.zeros_like(sc) for _ in range(world)]
+            dist.all_gather(allsc, sc)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t_start
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches = eng.launch_count - launches0
+    dev_s = (eng.device_ms_total - dev0) / 1e3  # CUDA-event time of every stage call in the region
+    ar_dev_ms = (dev_s * 1e3 - diff_ms - voc_ms) / args.steps
+
+    stats = torch.tensor([wall, dev_s, audio_s, float(n_tokens), ar_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        wall, dev_s, ar_wall = mx[0].item(), mx[1].item(), mx[4].item()
+        audio_total, tok_total = sm[2].item(), sm[3].item()
+    else:
+        audio_total, tok_total = audio_s, float(n_tokens)
+
+    # roofline of the dominant kernel (AR streaming GEMV), measured live with CUDA events
+    peak, peak_kind = measured_peaks()
+    by_tot = ms_tot = 0.0
+    per_op = {}
+    for op, name in enumerate(["qkv", "attn_proj", "fc", "mlp_proj"]):
+        ms, by = eng.bench_gemv(op, 1, 240)
+        per_op[name] = {"us": ms * 1e3, "GBs": by / ms / 1e6}
+        by_tot += by
+        ms_tot += ms
+    achieved = by_tot / ms_tot / 1e6
+    line = {
+        "metric": "real-time factor (audio-s/wall-s)", "value": audio_total / dev_s, "unit": "audio-s/wall-s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": workload_config(world),
+        "ar_mel_tokens_per_s": tok_total / ar_wall, "ar_mel_tokens_per_s_device": tok_total / (ar_dev_ms * args.steps / 1e3) if world == 1 else None,
+        "stage_ms": {"ar_wall": ar_wall / args.steps * 1e3, "ar_device": ar_dev_ms, "diffusion_device": diff_ms / args.steps,
+                     "vocoder_device": voc_ms / args.steps},
+        "e2e": {"value": audio_total / wall, "unit": "audio-s/wall-s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                     "kernel": "wsgemv_kernel<__half,1> (AR decode GEMV), bytes = K*N*2 + B*K*4 + B*N*4 + N*4 per launch",
+                     "per_op": per_op},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = run_reference_sample()
+            line["cpu_baseline"] = {"value": r["rtf"], "unit": "audio-s/wall-s", "cores": 4, "kind": "reference",
+                                    "sample": r["sample"], "host_cpus": os.cpu_count(),
+                                    "ar_mel_tokens_per_s": r["tok_s"]}
+        except Exception as e:  # the checker being unavailable must not hide the measurement
+            line["cpu_baseline"] = {"value": None, "unit": "audio-s/wall-s", "cores": 0, "kind": "reference",
+                                    "sample": f"unavailable: {e}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

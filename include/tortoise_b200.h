@@ -117,6 +117,8 @@ int tts_sync(tts_ctx *ctx);
 int64_t tts_launch_count(const tts_ctx *ctx);
 /* device-side duration in ms of the last tts_* stage call (CUDA events on the stream) */
 float tts_last_stage_ms(const tts_ctx *ctx);
+/* sum of the device-side durations of all stage calls since tts_init (CUDA events) */
+double tts_device_ms_total(const tts_ctx *ctx);
 /* micro-benchmark of the streaming GEMV kernel over all 30 layers' weights (what
  * bench.py's roofline figure is computed from): returns average ms per launch and the
  * algorithmic bytes per launch for the chosen op (0 qkv,1 attn-proj,2 fc,3 mlp-proj,4 lm-head) */

@@ -37,7 +37,7 @@ def test_prefill_and_teacher_forced_decode_b1(engine_f32, golden, voice):
     assert np.abs(lg[0] - g["logits_0"]).max() < LOGIT_TOL
     toks = _codes_to_steps(g["codes500"])
     steps = {int(k.split("_")[1]) for k in g.files if k.startswith("logits_")}
-    assert steps == set(range(len(toks) + 1))  # every decode step of the reference run is pinned
+    assert steps == set(range(len(toks)))  # every decode step of the reference run is pinned
     for i, t in enumerate(toks):
         lg = engine_f32.ar_step([t], i + 2)  # reference: fixed_position = i + 2 (main.cpp:5227)
         if (i + 1) in steps:

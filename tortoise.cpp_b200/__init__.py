@@ -79,6 +79,8 @@ def load_library() -> C.CDLL:
     lib.tts_launch_count.restype = C.c_int64
     lib.tts_last_stage_ms.argtypes = [vp]
     lib.tts_last_stage_ms.restype = C.c_float
+    lib.tts_device_ms_total.argtypes = [vp]
+    lib.tts_device_ms_total.restype = C.c_double
     lib.tts_bench_gemv.argtypes = [vp, i32, i32, i32, P(C.c_float), P(C.c_double)]
     _lib = lib
     return lib
@@ -205,6 +207,10 @@ class Engine:
     @property
     def last_stage_ms(self):
         return float(self.lib.tts_last_stage_ms(self.h))
+
+    @property
+    def device_ms_total(self):
+        return float(self.lib.tts_device_ms_total(self.h))
 
     def bench_gemv(self, op, B, iters):
         ms, by = C.c_float(), C.c_double()

@@ -299,6 +299,7 @@ void ar_prefill(tts_ctx *c, const int32_t *text, int T, const float *voice, int 
   TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  c->total_ms += c->last_ms;
   if (logits_out) memcpy(logits_out, s.h_logits, size_t(B) * kMelVocab * 4);
   s.B = B;
   s.T = T;
@@ -361,6 +362,7 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
   if (sync_out) {
     TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
     TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  c->total_ms += c->last_ms;
     if (logits_out) memcpy(logits_out, s.h_logits, size_t(B) * kMelVocab * 4);
   }
 }
@@ -429,6 +431,7 @@ void ar_latents(tts_ctx *c, const int32_t *text, int T, const float *voice, cons
   TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  c->total_ms += c->last_ms;
 }
 
 // Streaming-GEMV micro-benchmark over the 30 layers' weights (larger than L2 in total, so

@@ -360,6 +360,7 @@ void diff_eps(tts_ctx *c, const float *latents, int Lf, const float *x, int S, i
   TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  c->total_ms += c->last_ms;
   for (int t = 0; t < S; ++t)
     for (int ch = 0; ch < 200; ++ch) out[size_t(ch) * S + t] = h[size_t(t) * 200 + ch];
 }
@@ -400,6 +401,7 @@ void diff_sample(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, c
   TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  c->total_ms += c->last_ms;
   memcpy(mel, h, nx * 4);
 }
 

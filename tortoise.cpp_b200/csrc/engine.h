@@ -77,6 +77,7 @@ struct tts_ctx {
   std::string err;
   int64_t launches = 0;
   float last_ms = 0.f;
+  double total_ms = 0.0;  // device time of every stage call so far (CUDA events)
   bool use_graph = true;
   bool use_pdl = true;
   tts::ArModel ar;

@@ -134,6 +134,7 @@ int tts_sync(tts_ctx *c) { TTS_API_BODY(c, TTS_CUDA_TRY(cudaStreamSynchronize(c-
 
 int64_t tts_launch_count(const tts_ctx *c) { return c ? c->launches : 0; }
 float tts_last_stage_ms(const tts_ctx *c) { return c ? c->last_ms : 0.f; }
+double tts_device_ms_total(const tts_ctx *c) { return c ? c->total_ms : 0.0; }
 int tts_bench_gemv(tts_ctx *c, int32_t op, int32_t B, int32_t iters, float *ms, double *bytes) {
   TTS_API_BODY(c, if (!ms || !bytes || iters < 1) throw tts::ArgError("bad argument"); tts::ar_bench_gemv(c, op, B, iters, ms, bytes))
 }

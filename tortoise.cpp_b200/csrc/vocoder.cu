@@ -319,6 +319,7 @@ void voc_run(tts_ctx *c, const float *mel, int S, const float *noise, float *aud
   TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  c->total_ms += c->last_ms;
   memcpy(audio, m.h_pin, size_t(n_out) * 4);
 }
 

@@ -81,8 +81,16 @@ def _make_tensor(rng: np.random.Generator, fname: str, name: str, ne: list[int])
     # diffusion / vocoder matrices: roughly variance preserving
     fi = _fan_in(name, ne)
     gain = 0.8
+    # vocoder kernel predictor: its input is the denormalised mel (|values| up to 11.5) and its
+    # outputs are the LVC kernels that multiply 96 taps; keep the sigmoid/tanh gate
+    # pre-activations O(1) so the generator is well conditioned (with larger gains the
+    # network amplifies 1e-6 input perturbations to 1e-3 output NMSE -- useless for parity).
+    if "input_conv.0.weight" in name:
+        gain = 0.15
     if "kernel_conv.weight" in name:
-        gain = 0.35  # LVC kernels multiply 96 taps; keep the gate pre-activations O(1)
+        gain = 0.08
+    if "bias_conv.weight" in name:
+        gain = 0.3
     return normal(gain / np.sqrt(fi))
 
 
