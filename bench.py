@@ -39,8 +39,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PROMPT = "this is a test message."
-N_CODES = 35            # round(1.5 * len(PROMPT)) = 34.5 -> 35
-DIFF_STEPS = 80
+# profiling-only knobs (ncu replays every launch ~40x; a full 58k-launch step is not profilable):
+# the same code path with fewer repetitions.  Non-default values are flagged in `config`.
+N_CODES = int(os.environ.get("TTS_BENCH_CODES", "35"))          # round(1.5 * len(PROMPT)) = 34.5 -> 35
+DIFF_STEPS = int(os.environ.get("TTS_BENCH_DIFF_STEPS", "80"))
 MODEL_DIR = os.environ.get("TTS_MODEL_DIR", "/tmp/tortoise_b200_models")
 GOLDEN_MODELS = os.path.join(ROOT, "tests", "golden", "models")
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
@@ -185,6 +187,7 @@ def workload_config(world):
             "diffusion_steps": DIFF_STEPS, "weights": "seeded synthetic (tortoise.cpp_b200/synth_weights.py)",
             "l2_policy": "inputs larger than L2: 0.77 GB of f16 AR weights + 0.36 GB of diffusion weights are "
                          "re-streamed every step (L2 = 126 MB)",
+            "reduced_for_profiling": (N_CODES != 35 or DIFF_STEPS != 80),
             "parallelism": f"dp{world} (candidates sharded, weights replicated)"}
 
 
@@ -220,6 +223,7 @@ def main():
     import _pkg
     pkg = _pkg.import_pkg()
     hostmod = _pkg.import_sub("host")
+    distmod = _pkg.import_sub("dist")
     hl = hostmod.HostLib(full=True)
     eng = pkg.Engine(device=local_rank, dtype=pkg.DTYPE_F16, max_batch=2, max_positions=404, parity_quirks=True)
     eng.load_ar(os.path.join(MODEL_DIR, "ggml-model.bin"))
@@ -276,10 +280,8 @@ def main():
         n_tokens += steps
         h2d, d2h = bi, bo
         last_score = score
-        if world > 1:  # final candidate gather / selection (the path's only exchange)
-            sc = torch.tensor([score], device="cuda")
-            allsc = [torch.zeros_like(sc) for _ in range(world)]
-            dist.all_gather(allsc, sc)
+        if world > 1:  # final candidate gather / selection (the path's only exchange; NCCL)
+            winner, owner, _, _ = distmod.gather_select([score], [steps], device=torch.device("cuda", local_rank))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
