@@ -6,7 +6,7 @@
 
 #include "ar_kernels.cuh"
 #include "engine.h"
-#include "gemm.cuh"
+#include "gemm_launch.cuh"
 #include "wsgemv.cuh"
 
 namespace tts {
@@ -172,15 +172,8 @@ static GemvArgs gemv_args(const void *W, const float *bias, const float *in, flo
 static void launch_tgemm(tts_ctx *c, const Launcher &L, const __half *Ahi, const __half *Alo, const __half *Whi,
                          const __half *Wlo, const float *bias, float *C, __half *Chi, __half *Clo, int M, int N,
                          int K, int lda, int ldc, int ldh, int epi) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    TTS_CUDA_TRY(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(tgemm_smem_bytes())));
-    attr_done = true;
-  }
   TGemmArgs g{Ahi, Alo, Whi, Wlo, bias, C, Chi, Clo, M, N, K, lda, ldc, ldh, epi, 1, 1, 0, 0, M};
-  dim3 grid((N + TG_BN - 1) / TG_BN, (M + TG_BM - 1) / TG_BM);
-  L(tgemm_kernel, grid, dim3(128), tgemm_smem_bytes(), g);
+  launch_gemm(L, g);
 }
 
 // The lm-head on decode-shaped activations: logits = W . LN(LN(h) wf + bf) w0 + b0 (A-1)

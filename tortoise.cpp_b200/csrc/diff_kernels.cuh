@@ -59,9 +59,13 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x));
 // grid (T + 2*halo, nseq) x 256.
 static __global__ void __launch_bounds__(256) gn_apply_kernel(const float *X, const float *stats, const float *w,
                                                        const float *b, const float *ss, __half *out16,
-                                                       float *out32, int T, int halo, int ldo, int silu) {
+                                                       float *out32, int T, int halo, int ldo, int silu,
+                                                       const int *step_ptr, int ss_step_stride) {
   pdl_launch_dependents();
   pdl_wait();
+  // the per-timestep scale|shift table advances with a device-side step counter so that one
+  // captured CUDA graph serves every sampling step
+  if (ss && step_ptr) ss += size_t(*step_ptr) * ss_step_stride;
   const int row = blockIdx.x, seq = blockIdx.y, tid = threadIdx.x;
   const int t = row - halo;
   const int c = tid * 4;
@@ -286,12 +290,14 @@ struct DdpmCoef {
   float cfk, sqrt_recip, sqrt_recipm1, coef1, coef2, min_log, max_log;
   int last;
 };
-static __global__ void __launch_bounds__(256) ddpm_step_kernel(float *x, const float *OUT, const float *noise,
-                                                        const DdpmCoef *coefs, int step, int S) {
+static __global__ void __launch_bounds__(256) ddpm_step_kernel(float *x, const float *OUT, const float *noise_base,
+                                                        const DdpmCoef *coefs, const int *step_ptr, int S) {
   pdl_launch_dependents();
   pdl_wait();
+  const int step = *step_ptr;
   const DdpmCoef k = coefs[step];
   const int n = 100 * S;
+  const float *noise = noise_base + size_t(step + 1) * n;  // block 0 was the initial x
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int ch = i / S, t = i % S;
     const float eps_c = OUT[size_t(t) * 200 + ch];
@@ -309,6 +315,12 @@ static __global__ void __launch_bounds__(256) ddpm_step_kernel(float *x, const f
     if (!k.last) r = float(__dadd_rn(double(mean), __dmul_rn(exp(__dmul_rn(0.5, double(logvar))), double(noise[i]))));
     x[i] = r;
   }
+}
+
+static __global__ void step_inc_kernel(int *step_ptr) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) *step_ptr += 1;
 }
 
 // weight re-layout at load: conv weight f32 [OC][IC][K] (K fastest) -> f16 [K][OC][ICpad]

@@ -10,7 +10,7 @@
 
 #include "diff_kernels.cuh"
 #include "engine.h"
-#include "gemm.cuh"
+#include "gemm_launch.cuh"
 #include "host/host_math.h"
 
 namespace tts {
@@ -45,6 +45,10 @@ struct DiffModel {
   float *TE = nullptr, *T0 = nullptr, *TEMB = nullptr, *EMB = nullptr;
   __half *P_hi = nullptr, *P_lo = nullptr;  // [steps][1024] planes scratch
   DdpmCoef *coefs = nullptr;
+  int *d_step = nullptr;           // device-side sampling-step counter (graph replay)
+  cudaGraphExec_t step_graph = nullptr;
+  int graph_S = -1;
+  size_t noise_cap = 0;
   float *h_pin = nullptr;  // pinned staging for x / outputs
   size_t h_pin_bytes = 0;
   // cached conditioning
@@ -201,6 +205,8 @@ static void ensure_buffers(tts_ctx *c, int S, int steps) {
     grow(&m.ATTlo, s2 * kDim);
     grow(&m.rpb, size_t(S) + 8);
     grow(&m.up_idx, size_t(S));
+    if (!m.d_step) TTS_CUDA_TRY(cudaMalloc(&m.d_step, 4));
+    if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; m.graph_S = -1; }
     m.capS = S;
     m.cond_L = m.cond_S = -1;
   }
@@ -212,6 +218,7 @@ static void ensure_buffers(tts_ctx *c, int S, int steps) {
     grow(&m.P_hi, size_t(steps) * kDim);
     grow(&m.P_lo, size_t(steps) * kDim);
     grow(&m.coefs, size_t(steps));
+    if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; m.graph_S = -1; }
     m.capSteps = steps;
   }
 }
@@ -219,16 +226,9 @@ static void ensure_buffers(tts_ctx *c, int S, int steps) {
 static void tg(tts_ctx *c, const Launcher &L, const __half *Ahi, const __half *Alo, const __half *Whi, const __half *Wlo,
                const float *bias, float *C, int M, int N, int K, int lda, int ldc, int epi, int taps = 1, int T = 0,
                int halo = 0) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    TTS_CUDA_TRY(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(tgemm_smem_bytes())));
-    attr_done = true;
-  }
   TGemmArgs g{Ahi, Alo, Whi, Wlo, bias, C, nullptr, nullptr, M, N, K, lda, ldc, 0, epi, taps, 1, taps / 2, halo,
               T > 0 ? T : M};
-  dim3 grid((N + TG_BN - 1) / TG_BN, (M + TG_BM - 1) / TG_BM);
-  L(tgemm_kernel, grid, dim3(128), tgemm_smem_bytes(), g);
+  launch_gemm(L, g);
 }
 
 // f16 x f16 -> f32 convolution over nseq sequences of T frames (halo 1)
@@ -242,7 +242,7 @@ static void gn(tts_ctx *c, const Launcher &L, const float *X, const float *w, co
   DiffModel &m = *c->diff;
   L(gn_stats_kernel, dim3(32, nseq), dim3(256), 0, X, m.stats, T);
   L(gn_apply_kernel, dim3(T + 2, nseq), dim3(256), 0, X, (const float *)m.stats, w, b, ss, out16, out32, T, 1, kDim,
-    silu);
+    silu, (const int *)m.d_step, 16 * 2048);
 }
 
 // ResBlock (main.cpp:3347-3480): x += conv3(silu((GN(h)w+b)(1+scale)+shift)),
@@ -279,6 +279,7 @@ static void prepare_conditioning(tts_ctx *c, const Launcher &L, const float *lat
   conv(c, L, m.A16, m.lc_conv_w, m.lc_conv_b, m.CW, 1, Lf, kDim, kDim, 3, kDim, E_BIAS);
   for (int i = 0; i < 4; ++i) attn_block(c, L, m.lc[i], m.CW, 1, Lf);
   // code_norm, then * (1 + cond_latent[:1024]) + cond_latent[1024:]  (main.cpp:3293-3317)
+  // (cond_latent is not a per-step table: d_step is 0 whenever the conditioning branch runs)
   gn(c, L, m.CW, m.code_norm_w, m.code_norm_b, m.cond_latent, nullptr, m.H1, 1, Lf, 0);
   L(code_emb_kernel, dim3(S, 2), dim3(256), 0, (const float *)m.H1, (const int *)m.up_idx,
     (const float *)m.uncond_emb, m.CE, S);
@@ -348,6 +349,7 @@ void diff_eps(tts_ctx *c, const float *latents, int Lf, const float *x, int S, i
   ensure_buffers(c, S, 1);
   Launcher L{c->stream, c->use_pdl, &c->launches};
   TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  TTS_CUDA_TRY(cudaMemsetAsync(m.d_step, 0, 4, c->stream));
   prepare_conditioning(c, L, latents, Lf, S);
   prepare_time(c, L, {timestep});
   TTS_CUDA_TRY(cudaMemcpyAsync(m.x_dev, x, size_t(100) * S * 4, cudaMemcpyHostToDevice, c->stream));
@@ -373,6 +375,7 @@ void diff_sample(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, c
   Launcher L{c->stream, c->use_pdl, &c->launches};
   const size_t nx = size_t(100) * S;
   TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  TTS_CUDA_TRY(cudaMemsetAsync(m.d_step, 0, 4, c->stream));  // conditioning branch must see step 0
   const std::vector<tts_host::DdpmStep> sched = tts_host::ddpm_schedule(n_steps);
   std::vector<DdpmCoef> coefs(n_steps);
   std::vector<int> timesteps(n_steps);
@@ -385,16 +388,54 @@ void diff_sample(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, c
   prepare_conditioning(c, L, latents, Lf, S);
   prepare_time(c, L, timesteps);
   // noise: block 0 = initial x, block i+1 = the draw of step i (always drawn, used unless last)
-  if (m.noise_dev) cudaFree(m.noise_dev);
-  m.noise_dev = nullptr;
-  TTS_CUDA_TRY(cudaMalloc(&m.noise_dev, size_t(n_steps + 1) * nx * 4));
+  // (the graph embeds this pointer: reallocation drops the captured graph)
+  if (m.noise_cap < size_t(n_steps + 1) * nx) {
+    if (m.noise_dev) cudaFree(m.noise_dev);
+    m.noise_dev = nullptr;
+    TTS_CUDA_TRY(cudaMalloc(&m.noise_dev, size_t(n_steps + 1) * nx * 4));
+    m.noise_cap = size_t(n_steps + 1) * nx;
+    if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; m.graph_S = -1; }
+  }
   TTS_CUDA_TRY(cudaMemcpyAsync(m.noise_dev, noise, size_t(n_steps + 1) * nx * 4, cudaMemcpyHostToDevice, c->stream));
   TTS_CUDA_TRY(cudaMemcpyAsync(m.x_dev, m.noise_dev, nx * 4, cudaMemcpyDeviceToDevice, c->stream));
-  for (int i = 0; i < n_steps; ++i) {
+  // One sampling step = memcpy(code embedding) + ~165 kernels + DDPM update + step counter.
+  // Everything that varies per step is read through the device-side counter d_step, so the
+  // step is captured once into a CUDA graph and replayed n_steps times.
+  auto enqueue_step = [&](const Launcher &LL) {
     TTS_CUDA_TRY(cudaMemcpyAsync(m.CW, m.CE, size_t(2) * S * kDim * 4, cudaMemcpyDeviceToDevice, c->stream));
-    run_denoiser(c, L, 2, S, m.EMB + size_t(i) * 16 * 2048);
-    L(ddpm_step_kernel, dim3(std::min(148, int((nx + 255) / 256))), dim3(256), 0, m.x_dev, (const float *)m.OUT,
-      (const float *)(m.noise_dev + size_t(i + 1) * nx), (const DdpmCoef *)m.coefs, i, S);
+    run_denoiser(c, LL, 2, S, m.EMB);
+    LL(ddpm_step_kernel, dim3(std::min(148, int((nx + 255) / 256))), dim3(256), 0, m.x_dev, (const float *)m.OUT,
+       (const float *)m.noise_dev, (const DdpmCoef *)m.coefs, (const int *)m.d_step, S);
+    LL(step_inc_kernel, dim3(1), dim3(32), 0, m.d_step);
+  };
+  const int launches_per_step = 3 * (8 + 6) + 3 + 10 * (8 + 6) + 3 * 8 + 3 + 2;
+  if (c->use_graph) {
+    if (!m.step_graph || m.graph_S != S) {
+      if (m.step_graph) cudaGraphExecDestroy(m.step_graph);
+      m.step_graph = nullptr;
+      int64_t dummy = 0;
+      Launcher LG{c->stream, c->use_pdl, &dummy};
+      cudaGraph_t graph;
+      TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+      TTS_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        enqueue_step(LG);
+      } catch (...) {
+        cudaGraph_t g2;
+        cudaStreamEndCapture(c->stream, &g2);
+        throw;
+      }
+      TTS_CUDA_TRY(cudaStreamEndCapture(c->stream, &graph));
+      TTS_CUDA_TRY(cudaGraphInstantiate(&m.step_graph, graph, 0));
+      cudaGraphDestroy(graph);
+      m.graph_S = S;
+    }
+    TTS_CUDA_TRY(cudaMemsetAsync(m.d_step, 0, 4, c->stream));
+    for (int i = 0; i < n_steps; ++i) TTS_CUDA_TRY(cudaGraphLaunch(m.step_graph, c->stream));
+    c->launches += int64_t(n_steps) * launches_per_step;
+  } else {
+    TTS_CUDA_TRY(cudaMemsetAsync(m.d_step, 0, 4, c->stream));
+    for (int i = 0; i < n_steps; ++i) enqueue_step(L);
   }
   float *h = pin(c, nx * 4);
   TTS_CUDA_TRY(cudaMemcpyAsync(h, m.x_dev, nx * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -1,0 +1,55 @@
+// gemm_launch.cuh -- picks the tensor-core GEMM implementation for one TGemmArgs problem:
+// tcgen05/TMEM (tc5gemm.cuh) whenever K is a multiple of its 64-wide K block, otherwise the
+// HMMA (wmma) kernel.  TTS_NO_TCGEN05=1 forces the HMMA kernel (A/B testing, parity tests).
+#pragma once
+#include <stdlib.h>
+
+#include "tc5gemm.cuh"
+
+namespace tts {
+
+static inline bool tc5_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("TTS_NO_TCGEN05");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static inline void launch_gemm(const Launcher &L, const TGemmArgs &g) {
+  if (tc5_enabled() && g.K % T5_BK == 0) {
+    const bool alo = g.Alo != nullptr, wlo = g.Wlo != nullptr;
+    const int mt = (g.M + T5_BM - 1) / T5_BM;
+    // BN = 64 halves the A re-reads; BN = 32 doubles the CTA count when the grid would be small
+    const bool bn64 = ((g.N + 63) / 64) * mt >= 120;
+    // deep pipeline (8 x 20-24 KB stages) for single-plane operands (the convolutions): these
+    // GEMMs are small (M = 2S ~ 400 rows) and latency-bound; 4 stages when lo planes double a stage
+    const bool deep = !alo && !wlo;
+    auto go = [&](auto kern, int BN, int stages) {
+      TTS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        int(tc5_smem_bytes(BN, stages, true, true) > 227 * 1024
+                                                ? tc5_smem_bytes(BN, stages, alo, wlo)
+                                                : tc5_smem_bytes(BN, stages, true, true))));
+      L(kern, dim3((g.N + BN - 1) / BN, mt), dim3(T5_THREADS), tc5_smem_bytes(BN, stages, alo, wlo), g);
+    };
+    if (bn64) {
+      if (deep) go(tc5gemm_kernel<64, 8>, 64, 8);
+      else go(tc5gemm_kernel<64, 4>, 64, 4);
+    } else {
+      if (deep) go(tc5gemm_kernel<32, 8>, 32, 8);
+      else go(tc5gemm_kernel<32, 4>, 32, 4);
+    }
+    return;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    TTS_CUDA_TRY(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(tgemm_smem_bytes())));
+    attr_done = true;
+  }
+  dim3 grid((g.N + TG_BN - 1) / TG_BN, (g.M + TG_BM - 1) / TG_BM);
+  L(tgemm_kernel, grid, dim3(128), tgemm_smem_bytes(), g);
+}
+
+}  // namespace tts

@@ -8,7 +8,7 @@
 
 #include "diff_kernels.cuh"
 #include "engine.h"
-#include "gemm.cuh"
+#include "gemm_launch.cuh"
 
 namespace tts {
 
@@ -231,15 +231,8 @@ static void vgrow(T **p, size_t n) {
 
 static void vtg(tts_ctx *c, const Launcher &L, const __half *X16, const __half *W, const float *bias, float *C, int M,
                 int N, int K, int ldc, int epi, int taps, int dil, int pad, int halo, int T) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    TTS_CUDA_TRY(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(tgemm_smem_bytes())));
-    attr_done = true;
-  }
   TGemmArgs g{X16, nullptr, W, nullptr, bias, C, nullptr, nullptr, M, N, K, K, ldc, 0, epi, taps, dil, pad, halo, T};
-  dim3 grid((N + TG_BN - 1) / TG_BN, (M + TG_BM - 1) / TG_BM);
-  L(tgemm_kernel, grid, dim3(128), tgemm_smem_bytes(), g);
+  launch_gemm(L, g);
 }
 
 void voc_run(tts_ctx *c, const float *mel, int S, const float *noise, float *audio) {
