@@ -20,9 +20,10 @@ static inline bool tc5_enabled() {
 static inline void launch_gemm(const Launcher &L, const TGemmArgs &g) {
   if (tc5_enabled() && g.K % T5_BK == 0) {
     const bool alo = g.Alo != nullptr, wlo = g.Wlo != nullptr;
-    const int mt = (g.M + T5_BM - 1) / T5_BM;
+    const int nseq = g.M / g.T;                      // M = nseq * T always
+    const int mt = (g.T + T5_BM - 1) / T5_BM;        // tiles per sequence
     // BN = 64 halves the A re-reads; BN = 32 doubles the CTA count when the grid would be small
-    const bool bn64 = ((g.N + 63) / 64) * mt >= 120;
+    const bool bn64 = ((g.N + 63) / 64) * mt * nseq >= 120;  // measured: BN = 32 (more CTAs) wins for N = 1024
     // deep pipeline (8 x 20-24 KB stages) for single-plane operands (the convolutions): these
     // GEMMs are small (M = 2S ~ 400 rows) and latency-bound; 4 stages when lo planes double a stage
     const bool deep = !alo && !wlo;
@@ -31,7 +32,7 @@ static inline void launch_gemm(const Launcher &L, const TGemmArgs &g) {
                                         int(tc5_smem_bytes(BN, stages, true, true) > 227 * 1024
                                                 ? tc5_smem_bytes(BN, stages, alo, wlo)
                                                 : tc5_smem_bytes(BN, stages, true, true))));
-      L(kern, dim3((g.N + BN - 1) / BN, mt), dim3(T5_THREADS), tc5_smem_bytes(BN, stages, alo, wlo), g);
+      L(kern, dim3((g.N + BN - 1) / BN, mt, nseq), dim3(T5_THREADS), tc5_smem_bytes(BN, stages, alo, wlo), g);
     };
     if (bn64) {
       if (deep) go(tc5gemm_kernel<64, 8>, 64, 8);

@@ -25,7 +25,7 @@ __host__ __device__ inline size_t tc5_stage_bytes(int BN, bool alo, bool wlo) {
   return size_t(T5_BM) * 128 * (alo ? 2 : 1) + size_t(BN) * 128 * (wlo ? 2 : 1);
 }
 __host__ __device__ inline size_t tc5_smem_bytes(int BN, int stages, bool alo, bool wlo) {
-  return stages * tc5_stage_bytes(BN, alo, wlo) + 1024 /*alignment slack*/ + 256 /*barriers*/ + 1024 /*row table*/;
+  return stages * tc5_stage_bytes(BN, alo, wlo) + 1024 /*alignment slack*/ + 256 /*barriers*/;
 }
 
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -77,10 +77,13 @@ static __global__ void __launch_bounds__(T5_THREADS) tc5gemm_kernel(TGemmArgs g)
   uint64_t *empty = full + T5_STAGES;
   uint64_t *done = empty + T5_STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
-  long *arow_tab = reinterpret_cast<long *>(tmem_slot + 2);  // [128] A row index (before tap shift) or -1
 
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-  const int m0 = blockIdx.y * T5_BM, n0 = blockIdx.x * BN;
+  // M tiles never straddle sequences: tile rows are contiguous rows of ONE sequence of the
+  // (halo-padded) activation buffer, so loader addresses advance by a constant stride.
+  const int seq = blockIdx.z, t0 = blockIdx.y * T5_BM;
+  const int rows_valid = min(T5_BM, g.T - t0);  // rows of this tile that exist
+  const int m0 = seq * g.T + t0, n0 = blockIdx.x * BN;
   const int kchunks = g.K / T5_BK;
   const int iters = g.taps * kchunks;
 
@@ -91,15 +94,6 @@ static __global__ void __launch_bounds__(T5_THREADS) tc5gemm_kernel(TGemmArgs g)
     }
     mbar_init(done, 1);
     fence_barrier_init();
-  }
-  if (tid < T5_BM) {
-    const int m = m0 + tid;
-    long r = -1;
-    if (m < g.M) {
-      const int seq = m / g.T, t = m % g.T;
-      r = long(seq) * (g.T + 2 * g.halo) + t + g.halo - g.pad;
-    }
-    arow_tab[tid] = r;
   }
   if (warp == T5_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -125,30 +119,42 @@ static __global__ void __launch_bounds__(T5_THREADS) tc5gemm_kernel(TGemmArgs g)
     // latency-bound GEMMs).  Lane l moves 16-byte chunk (l & 7) of rows (l >> 3) + 4 j.
     if (warp < T5_STAGES) {
       const int s = warp;
-      const int c = lane & 7;
+      const int c = lane & 7, r0 = lane >> 3;  // lane moves chunk c of rows r0 + 4 j
       unsigned char *sp = stage_ptr(s);
       unsigned char *wbase = sp + a_bytes * (has_alo ? 2 : 1);
+      // (r & 7) alternates between r0 and r0 + 4 as j advances: two swizzled chunk offsets
+      const uint32_t sw_even = uint32_t((c ^ r0) * 16), sw_odd = uint32_t((c ^ (r0 + 4)) * 16);
+      const size_t a_first = (size_t(seq) * (g.T + 2 * g.halo) + t0 + g.halo - g.pad + r0) * g.lda + c * 8;
+      const size_t a_step = size_t(4) * g.lda;
       for (int it = warp, round = 0; it < iters; it += T5_STAGES, ++round) {
         mbar_wait(&empty[s], (round & 1) ^ 1);
         const int tap = it / kchunks, k0 = (it % kchunks) * T5_BK;
-#pragma unroll 4
+        const __half *ap = g.Ahi + a_first + size_t(tap) * g.dil * g.lda + k0;
+        const __half *alp = has_alo ? g.Alo + a_first + size_t(tap) * g.dil * g.lda + k0 : nullptr;
+        unsigned char *d = sp + r0 * 128;
+#pragma unroll 8
         for (int j = 0; j < T5_BM / 4; ++j) {
-          const int r = (lane >> 3) + 4 * j;
-          const long ar = arow_tab[r];
-          const size_t aoff = size_t((ar < 0 ? 0 : ar) + tap * g.dil) * g.lda + k0 + c * 8;
-          unsigned char *d = sp + r * 128 + ((c ^ (r & 7)) * 16);
-          cp_async16(d, g.Ahi + aoff, ar < 0 ? 0 : 16);
-          if (has_alo) cp_async16(d + a_bytes, g.Alo + aoff, ar < 0 ? 0 : 16);
+          const int ok = (r0 + 4 * j) < rows_valid ? 16 : 0;
+          unsigned char *dd = d + ((j & 1) ? sw_odd : sw_even);
+          cp_async16(dd, ok ? ap : g.Ahi, ok);
+          if (has_alo) cp_async16(dd + a_bytes, ok ? alp : g.Alo, ok);
+          ap += a_step;
+          if (has_alo) alp += a_step;
+          d += 4 * 128;
         }
-#pragma unroll 4
+        const size_t w_first = (size_t(tap) * g.N + n0 + r0) * g.K + k0 + c * 8;
+        const __half *wp = g.Whi + w_first;
+        const __half *wlp = has_wlo ? g.Wlo + w_first : nullptr;
+        d = wbase + r0 * 128;
+#pragma unroll 8
         for (int j = 0; j < BN / 4; ++j) {
-          const int r = (lane >> 3) + 4 * j;
-          const int n = n0 + r;
-          const int nc = min(n, g.N - 1);
-          const size_t woff = (size_t(tap) * g.N + nc) * g.K + k0 + c * 8;
-          unsigned char *d = wbase + r * 128 + ((c ^ (r & 7)) * 16);
-          cp_async16(d, g.Whi + woff, n < g.N ? 16 : 0);
-          if (has_wlo) cp_async16(d + b_bytes, g.Wlo + woff, n < g.N ? 16 : 0);
+          const int ok = (n0 + r0 + 4 * j) < g.N ? 16 : 0;
+          unsigned char *dd = d + ((j & 1) ? sw_odd : sw_even);
+          cp_async16(dd, ok ? wp : g.Whi, ok);
+          if (has_wlo) cp_async16(dd + b_bytes, ok ? wlp : g.Wlo, ok);
+          wp += size_t(4) * g.K;
+          if (has_wlo) wlp += size_t(4) * g.K;
+          d += 4 * 128;
         }
         cp_async_commit();
         cp_async_wait<0>();
@@ -161,14 +167,15 @@ static __global__ void __launch_bounds__(T5_THREADS) tc5gemm_kernel(TGemmArgs g)
     mbar_wait(done, 0);
     tc5_fence_after();
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;  // TMEM lane == tile row
+    const int row_in_tile = q * 32 + lane;  // TMEM lane == tile row
+    const int m = m0 + row_in_tile;
 #pragma unroll
     for (int cb = 0; cb < BN; cb += 32) {
       if (((cb / 32) & 1) != (warp >> 2) && BN > 32) continue;  // BN = 64: warps 0-3 cols 0-31, 4-7 cols 32-63
       if (BN == 32 && warp >= 4) continue;
       float v[32];
       tmem_ld32(tmem_d + (uint32_t(q * 32) << 16) + cb, v);
-      if (m < g.M) {
+      if (row_in_tile < rows_valid) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const int n = n0 + cb + j;
