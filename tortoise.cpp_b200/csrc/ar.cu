@@ -8,6 +8,7 @@
 #include "engine.h"
 #include "gemm_launch.cuh"
 #include "wsgemv.cuh"
+#include "ar_mega.cuh"
 
 namespace tts {
 
@@ -127,6 +128,22 @@ void ar_load(tts_ctx *c, const char *path) {
   TTS_CUDA_TRY(cudaMallocHost(&s.h_logits, B * kMelVocab * 4));
   TTS_CUDA_TRY(cudaMalloc(&s.d_text, 1024 * 4));
   TTS_CUDA_TRY(cudaMalloc(&s.d_voice, kDim * 4));
+  {
+    std::vector<MegaLayer> ml(kLayers);
+    for (int i = 0; i < kLayers; ++i) {
+      const ArLayer &l = m.layers[i];
+      ml[i] = MegaLayer{l.ln1_w, l.ln1_b, l.ln2_w, l.ln2_b, l.w_qkv, l.w_proj, l.w_fc, l.w_proj2,
+                        l.b_qkv,  l.b_proj, l.b_fc,  l.b_proj2};
+    }
+    TTS_CUDA_TRY(cudaMalloc(&m.mega_layers, sizeof(MegaLayer) * kLayers));
+    TTS_CUDA_TRY(cudaMemcpy(m.mega_layers, ml.data(), sizeof(MegaLayer) * kLayers, cudaMemcpyHostToDevice));
+    TTS_CUDA_TRY(cudaMalloc(&m.mega_bar, 2 * sizeof(unsigned int)));
+    const char *tr = getenv("TTS_MEGA_TRACE");
+    if (tr && tr[0] == '1') {
+      TTS_CUDA_TRY(cudaMalloc(&m.mega_dbg, 2000 * sizeof(long long)));
+      TTS_CUDA_TRY(cudaMemset(m.mega_dbg, 0, 2000 * sizeof(long long)));
+    }
+  }
   m.loaded = true;
 }
 
@@ -211,6 +228,33 @@ static void enqueue_step(tts_ctx *c, const Launcher &L, int B) {
     launch_gemv(c, L, gemv_args(l.w_proj2, l.b_proj2, s.m, s.h, kDim, kFF, B, PRO_NONE, EPI_RESID));
   }
   enqueue_lm_head(c, L, B);
+}
+
+// One decode step = one cooperative launch of the persistent kernel (ar_mega.cuh).
+template <typename WT>
+static void launch_mega_t(tts_ctx *c, int B, int n_past, int pos_id) {
+  ArModel &m = c->ar;
+  ArState &s = c->ars;
+  MegaArgs a{};
+  a.layers = (const MegaLayer *)m.mega_layers;
+  a.lnf_w = m.lnf_w; a.lnf_b = m.lnf_b; a.lm0_w = m.lm0_w; a.lm0_b = m.lm0_b; a.lm_b = m.lm_b; a.lm_w = m.lm_w;
+  a.mel_emb = m.mel_emb; a.mel_pos = m.mel_pos; a.tokens = s.d_tokens;
+  a.h = s.h; a.q = s.q; a.attn = s.attn; a.m = s.m; a.logits = s.logits; a.kc = s.kc; a.vc = s.vc;
+  a.dbg = m.mega_dbg;
+  a.bar = m.mega_bar; a.B = B; a.Bmax = s.Bmax; a.P = s.P; a.n_past = n_past; a.pos_id = pos_id;
+  static bool attr1 = false, attr2 = false;
+  void *args[] = {&a};
+  const size_t smem = mega_smem_bytes();
+  if (B == 1) {
+    auto k = ar_decode_mega_kernel<WT, 1>;
+    if (!attr1) { TTS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr1 = true; }
+    TTS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k, dim3(c->num_sms), dim3(MG_THREADS), args, smem, c->stream));
+  } else {
+    auto k = ar_decode_mega_kernel<WT, 2>;
+    if (!attr2) { TTS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr2 = true; }
+    TTS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k, dim3(c->num_sms), dim3(MG_THREADS), args, smem, c->stream));
+  }
+  c->launches += 1;
 }
 
 static void ensure_rows(tts_ctx *c, size_t rows) {
@@ -339,7 +383,13 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
   s.h_state[1] = pos_id;
   const int launches_per_step = 2 + kLayers * 5;
   TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-  if (c->use_graph) {
+  if (c->use_mega && s.P <= 1024) {
+    TTS_CUDA_TRY(cudaMemcpyAsync(s.d_tokens, s.h_tokens, B * 4, cudaMemcpyHostToDevice, c->stream));
+    TTS_CUDA_TRY(cudaMemsetAsync(c->ar.mega_bar, 0, 2 * sizeof(unsigned int), c->stream));
+    if (c->ar.dtype == TTS_DTYPE_F16) launch_mega_t<__half>(c, B, s.n_past, pos_id);
+    else launch_mega_t<float>(c, B, s.n_past, pos_id);
+    TTS_CUDA_TRY(cudaMemcpyAsync(s.h_logits, s.logits, size_t(B) * kMelVocab * 4, cudaMemcpyDeviceToHost, c->stream));
+  } else if (c->use_graph) {
     if (!s.step_graph || s.step_graph_B != B) build_step_graph(c, B);
     TTS_CUDA_TRY(cudaGraphLaunch(s.step_graph, c->stream));
     c->launches += launches_per_step;
@@ -357,6 +407,12 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
     TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   c->total_ms += c->last_ms;
     if (logits_out) memcpy(logits_out, s.h_logits, size_t(B) * kMelVocab * 4);
+    if (c->ar.mega_dbg && getenv("TTS_MEGA_TRACE_DUMP")) {
+      std::vector<long long> t(2000);
+      cudaMemcpy(t.data(), c->ar.mega_dbg, 2000 * sizeof(long long), cudaMemcpyDeviceToHost);
+      for (int i = 1; i < 1000 && t[2 * i] != 0; ++i)
+        fprintf(stderr, "trace %3d tag %2lld dt %6lld\n", i, t[2 * i], t[2 * i + 1] - t[2 * i - 1]);
+    }
   }
 }
 

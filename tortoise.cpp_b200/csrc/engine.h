@@ -43,6 +43,9 @@ struct ArModel {
   void *lm_w;  // [8194][1024]
   float *text_emb, *text_pos, *mel_emb, *mel_pos;
   size_t decode_weight_bytes = 0;
+  void *mega_layers = nullptr;   // device MegaLayer[30] (ar_mega.cuh)
+  unsigned int *mega_bar = nullptr;
+  long long *mega_dbg = nullptr;  // device trace buffer (TTS_MEGA_TRACE=1)
 };
 
 struct ArState {
@@ -80,6 +83,7 @@ struct tts_ctx {
   double total_ms = 0.0;  // device time of every stage call so far (CUDA events)
   bool use_graph = true;
   bool use_pdl = true;
+  bool use_mega = true;   // persistent single-kernel decode step (TTS_NO_MEGA=1 -> per-op graph path)
   tts::ArModel ar;
   tts::ArState ars;
   tts::DiffModel *diff = nullptr;

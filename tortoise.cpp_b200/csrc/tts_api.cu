@@ -69,6 +69,8 @@ int tts_init(const tts_config *cfg, tts_ctx **out) {
   c->use_graph = !(eg && eg[0] == '1');
   const char *ep = getenv("TTS_NO_PDL");
   c->use_pdl = !(ep && ep[0] == '1');
+  const char *em = getenv("TTS_NO_MEGA");
+  c->use_mega = !(em && em[0] == '1');
   try {
     TTS_CUDA_TRY(cudaSetDevice(cfg->device));
     TTS_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
