@@ -102,6 +102,13 @@ int tts_diffusion_eps(tts_ctx *ctx, const float *latents, int32_t L, const float
 int tts_diffusion_sample(tts_ctx *ctx, const float *latents, int32_t L, int32_t S,
                          int32_t n_steps, const float *noise, float *mel_out_100xS);
 
+/* Streaming form of the same loop, so the host can draw noise block i+1 (reference RNG order)
+ * while the GPU runs step i: begin(x0 = first 100*S draws) ; n_steps x step(next 100*S draws,
+ * asynchronous) ; end(mel_out) blocks.  tts_diffusion_sample == begin + steps + end. */
+int tts_diffusion_begin(tts_ctx *ctx, const float *latents, int32_t L, int32_t S, int32_t n_steps, const float *x0);
+int tts_diffusion_step(tts_ctx *ctx, const float *noise_block_100xS);
+int tts_diffusion_end(tts_ctx *ctx, float *mel_out_100xS);
+
 /* ---- vocoder stage ----------------------------------------------------------------- */
 /* Replaces vocoder_graph + compute (main.cpp:6078-6122): mel [100][S] NORMALISED
  * (denormalisation main.cpp:5575 is done on the device), noise [(S+10)][64] as drawn by
@@ -124,6 +131,11 @@ double tts_device_ms_total(const tts_ctx *ctx);
  * algorithmic bytes per launch for the chosen op (0 qkv,1 attn-proj,2 fc,3 mlp-proj,4 lm-head) */
 int tts_bench_gemv(tts_ctx *ctx, int32_t op, int32_t B, int32_t iters, float *ms_per_launch,
                    double *bytes_per_launch);
+
+/* `iters` consecutive decode steps (after tts_ar_prefill) timed with CUDA events on the stream,
+ * no host round trip in between: average ms per step and the algorithmic bytes of one step
+ * (streamed weights + KV read/append + embeddings + logits). */
+int tts_bench_decode_step(tts_ctx *ctx, int32_t iters, float *ms_per_step, double *bytes_per_step);
 
 #ifdef __cplusplus
 }

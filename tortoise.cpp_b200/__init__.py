@@ -81,6 +81,7 @@ def load_library() -> C.CDLL:
     lib.tts_last_stage_ms.restype = C.c_float
     lib.tts_device_ms_total.argtypes = [vp]
     lib.tts_device_ms_total.restype = C.c_double
+    lib.tts_bench_decode_step.argtypes = [vp, i32, P(C.c_float), P(C.c_double)]
     lib.tts_bench_gemv.argtypes = [vp, i32, i32, i32, P(C.c_float), P(C.c_double)]
     _lib = lib
     return lib
@@ -211,6 +212,11 @@ class Engine:
     @property
     def device_ms_total(self):
         return float(self.lib.tts_device_ms_total(self.h))
+
+    def bench_decode_step(self, iters):
+        ms, by = C.c_float(), C.c_double()
+        self._chk(self.lib.tts_bench_decode_step(self.h, iters, C.byref(ms), C.byref(by)))
+        return ms.value, by.value
 
     def bench_gemv(self, op, B, iters):
         ms, by = C.c_float(), C.c_double()

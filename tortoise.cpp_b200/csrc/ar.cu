@@ -483,6 +483,38 @@ void ar_latents(tts_ctx *c, const int32_t *text, int T, const float *voice, cons
   c->total_ms += c->last_ms;
 }
 
+// Decode-step benchmark: `iters` consecutive steps (persistent kernel or per-op graph, whatever
+// the context is configured for) between two CUDA events, no host round trip in between.
+// bytes = algorithmic bytes of one step at the mean KV length: streamed weights + embeddings
+// + KV read/append + logits.
+void ar_bench_step(tts_ctx *c, int iters, float *ms, double *bytes) {
+  ArState &s = c->ars;
+  if (!c->ar.loaded || s.B == 0) throw ArgError("tts_bench_decode_step before tts_ar_prefill");
+  if (iters < 1 || s.n_past + iters > s.P) throw ArgError("not enough KV slots for the requested iterations", TTS_ELIMIT);
+  std::vector<int32_t> toks(s.B, 100);
+  const int n0 = s.n_past;
+  ar_step(c, toks.data(), 2, nullptr, false);  // warm-up (graph build / attribute setup)
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  cudaEvent_t e0, e1;
+  TTS_CUDA_TRY(cudaEventCreate(&e0));
+  TTS_CUDA_TRY(cudaEventCreate(&e1));
+  TTS_CUDA_TRY(cudaEventRecord(e0, c->stream));
+  for (int i = 1; i < iters; ++i) ar_step(c, toks.data(), 2 + (i % 500), nullptr, false);
+  TTS_CUDA_TRY(cudaEventRecord(e1, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  float t = 0;
+  TTS_CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const int timed = iters - 1;
+  *ms = timed > 0 ? t / timed : 0.f;
+  const double n_mean = n0 + 1 + 0.5 * iters;
+  const double B = s.B;
+  *bytes = double(c->ar.decode_weight_bytes) + 2.0 * kLayers * kDim * B * (n_mean + 1) * 2.0 /*KV read, f16*/ +
+           2.0 * kLayers * kDim * B * 2.0 /*KV append*/ + (B + 1) * kDim * 4.0 /*embedding rows*/ +
+           double(kMelVocab) * B * 4.0 /*logits*/;
+}
+
 // Streaming-GEMV micro-benchmark over the 30 layers' weights (larger than L2 in total, so
 // every launch streams from HBM): average launch time from CUDA events on the stream.
 void ar_bench_gemv(tts_ctx *c, int op, int B, int iters, float *ms, double *bytes) {

@@ -49,6 +49,7 @@ struct DiffModel {
   cudaGraphExec_t step_graph = nullptr;
   int graph_S = -1;
   size_t noise_cap = 0;
+  int run_S = 0, run_steps = 0, run_i = -1;  // streaming sampler state
   float *h_pin = nullptr;  // pinned staging for x / outputs
   size_t h_pin_bytes = 0;
   // cached conditioning
@@ -367,7 +368,10 @@ void diff_eps(tts_ctx *c, const float *latents, int Lf, const float *x, int S, i
     for (int ch = 0; ch < 200; ++ch) out[size_t(ch) * S + t] = h[size_t(t) * 200 + ch];
 }
 
-void diff_sample(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, const float *noise, float *mel) {
+// Streaming form of the sampling loop: begin (conditioning, schedule, x0) / step (upload the
+// step's noise block, enqueue the captured step graph -- asynchronous) / end (read the mel).
+// The host draws noise block i+1 from the reference's RNG stream while the GPU runs step i.
+void diff_begin(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, const float *x0) {
   check_sizes(c, Lf, S);
   if (n_steps < 1 || n_steps > 4000) throw ArgError("bad n_steps");
   DiffModel &m = *c->diff;
@@ -396,8 +400,25 @@ void diff_sample(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, c
     m.noise_cap = size_t(n_steps + 1) * nx;
     if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; m.graph_S = -1; }
   }
-  TTS_CUDA_TRY(cudaMemcpyAsync(m.noise_dev, noise, size_t(n_steps + 1) * nx * 4, cudaMemcpyHostToDevice, c->stream));
+  float *hp = pin(c, size_t(n_steps + 1) * nx * 4);
+  memcpy(hp, x0, nx * 4);
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.noise_dev, hp, nx * 4, cudaMemcpyHostToDevice, c->stream));
   TTS_CUDA_TRY(cudaMemcpyAsync(m.x_dev, m.noise_dev, nx * 4, cudaMemcpyDeviceToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemsetAsync(m.d_step, 0, 4, c->stream));
+  m.run_S = S;
+  m.run_steps = n_steps;
+  m.run_i = 0;
+}
+
+void diff_step(tts_ctx *c, const float *noise_block) {
+  if (!c->diff || c->diff->run_i < 0 || c->diff->run_i >= c->diff->run_steps) throw ArgError("tts_diffusion_step out of sequence");
+  DiffModel &m = *c->diff;
+  const int S = m.run_S, i = m.run_i;
+  const size_t nx = size_t(100) * S;
+  Launcher L{c->stream, c->use_pdl, &c->launches};
+  float *hp = m.h_pin + size_t(i + 1) * nx;  // pinned slot of this block (stable until the copy ran)
+  memcpy(hp, noise_block, nx * 4);
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.noise_dev + size_t(i + 1) * nx, hp, nx * 4, cudaMemcpyHostToDevice, c->stream));
   // One sampling step = memcpy(code embedding) + ~165 kernels + DDPM update + step counter.
   // Everything that varies per step is read through the device-side counter d_step, so the
   // step is captured once into a CUDA graph and replayed n_steps times.
@@ -416,6 +437,7 @@ void diff_sample(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, c
       int64_t dummy = 0;
       Launcher LG{c->stream, c->use_pdl, &dummy};
       cudaGraph_t graph;
+      // capture must not record work that should run now: drain, then record one step
       TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
       TTS_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
       try {
@@ -430,20 +452,35 @@ void diff_sample(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, c
       cudaGraphDestroy(graph);
       m.graph_S = S;
     }
-    TTS_CUDA_TRY(cudaMemsetAsync(m.d_step, 0, 4, c->stream));
-    for (int i = 0; i < n_steps; ++i) TTS_CUDA_TRY(cudaGraphLaunch(m.step_graph, c->stream));
-    c->launches += int64_t(n_steps) * launches_per_step;
+    TTS_CUDA_TRY(cudaGraphLaunch(m.step_graph, c->stream));
+    c->launches += launches_per_step;
   } else {
-    TTS_CUDA_TRY(cudaMemsetAsync(m.d_step, 0, 4, c->stream));
-    for (int i = 0; i < n_steps; ++i) enqueue_step(L);
+    enqueue_step(L);
   }
-  float *h = pin(c, nx * 4);
+  m.run_i += 1;
+}
+
+void diff_end(tts_ctx *c, float *mel) {
+  if (!c->diff || c->diff->run_i != c->diff->run_steps || c->diff->run_steps <= 0) throw ArgError("tts_diffusion_end before all steps ran");
+  DiffModel &m = *c->diff;
+  const size_t nx = size_t(100) * m.run_S;
+  float *h = m.h_pin;  // slot 0 (x0 copy long done)
   TTS_CUDA_TRY(cudaMemcpyAsync(h, m.x_dev, nx * 4, cudaMemcpyDeviceToHost, c->stream));
   TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   c->total_ms += c->last_ms;
   memcpy(mel, h, nx * 4);
+  m.run_i = -1;
+  m.run_steps = 0;
+}
+
+void diff_sample(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, const float *noise, float *mel) {
+  check_sizes(c, Lf, S);
+  const size_t nx = size_t(100) * S;
+  diff_begin(c, latents, Lf, S, n_steps, noise);
+  for (int i = 0; i < n_steps; ++i) diff_step(c, noise + size_t(i + 1) * nx);
+  diff_end(c, mel);
 }
 
 }  // namespace tts

@@ -102,12 +102,16 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
 void ar_latents(tts_ctx *c, const int32_t *text, int T, const float *voice, const int32_t *codes, int B,
                 int n_keep, float *out);
 void ar_bench_gemv(tts_ctx *c, int op, int B, int iters, float *ms, double *bytes);
+void ar_bench_step(tts_ctx *c, int iters, float *ms, double *bytes);
 void ar_free(tts_ctx *c);
 // implemented in diffusion.cu / vocoder.cu
 void diff_load(tts_ctx *c, const char *path);
 void diff_eps(tts_ctx *c, const float *latents, int L, const float *x, int S, int timestep, int cond_free,
               float *out);
 void diff_sample(tts_ctx *c, const float *latents, int L, int S, int n_steps, const float *noise, float *mel);
+void diff_begin(tts_ctx *c, const float *latents, int L, int S, int n_steps, const float *x0);
+void diff_step(tts_ctx *c, const float *noise_block);
+void diff_end(tts_ctx *c, float *mel);
 void diff_free(tts_ctx *c);
 void voc_load(tts_ctx *c, const char *path);
 void voc_run(tts_ctx *c, const float *mel, int S, const float *noise, float *audio);

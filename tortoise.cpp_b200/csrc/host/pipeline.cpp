@@ -101,9 +101,18 @@ int tts_host_diffusion(struct tts_ctx *ctx, tts_rng *rng, const float *latents, 
   // RNG order: initial x (main.cpp:5638), then one block per step (main.cpp:6020), drawn every
   // step including the last.  Nothing else consumes the generator in between, so drawing the
   // blocks up front is the same stream.
-  std::vector<float> noise((size_t(n_steps) + 1) * nx);
-  for (size_t i = 0; i < noise.size(); ++i) noise[i] = rng->r.normal(rng->r.generator);
-  return tts_diffusion_sample(ctx, latents, L, S, n_steps, noise.data(), mel_out);
+  // Nothing else consumes the generator in between, so the stream equals the reference's; the
+  // blocks are drawn one step ahead of the GPU (tts_diffusion_step is asynchronous).
+  std::vector<float> blk(nx);
+  for (size_t i = 0; i < nx; ++i) blk[i] = rng->r.normal(rng->r.generator);
+  int rc = tts_diffusion_begin(ctx, latents, L, S, n_steps, blk.data());
+  if (rc != TTS_OK) return rc;
+  for (int s = 0; s < n_steps; ++s) {
+    for (size_t i = 0; i < nx; ++i) blk[i] = rng->r.normal(rng->r.generator);
+    rc = tts_diffusion_step(ctx, blk.data());
+    if (rc != TTS_OK) return rc;
+  }
+  return tts_diffusion_end(ctx, mel_out);
 }
 
 int tts_host_vocoder(struct tts_ctx *ctx, tts_rng *rng, const float *mel, int S, float *audio_out) {

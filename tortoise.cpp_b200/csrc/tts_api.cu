@@ -129,6 +129,15 @@ int tts_diffusion_sample(tts_ctx *c, const float *latents, int32_t L, int32_t S,
   TTS_API_BODY(c, if (!latents || !noise || !mel) throw tts::ArgError("null argument");
                tts::diff_sample(c, latents, L, S, n_steps, noise, mel))
 }
+int tts_diffusion_begin(tts_ctx *c, const float *latents, int32_t L, int32_t S, int32_t n_steps, const float *x0) {
+  TTS_API_BODY(c, if (!latents || !x0) throw tts::ArgError("null argument"); tts::diff_begin(c, latents, L, S, n_steps, x0))
+}
+int tts_diffusion_step(tts_ctx *c, const float *noise_block) {
+  TTS_API_BODY(c, if (!noise_block) throw tts::ArgError("null argument"); tts::diff_step(c, noise_block))
+}
+int tts_diffusion_end(tts_ctx *c, float *mel) {
+  TTS_API_BODY(c, if (!mel) throw tts::ArgError("null argument"); tts::diff_end(c, mel))
+}
 int tts_vocoder(tts_ctx *c, const float *mel, int32_t S, const float *noise, float *audio) {
   TTS_API_BODY(c, if (!mel || !noise || !audio) throw tts::ArgError("null argument"); tts::voc_run(c, mel, S, noise, audio))
 }
@@ -139,6 +148,10 @@ float tts_last_stage_ms(const tts_ctx *c) { return c ? c->last_ms : 0.f; }
 double tts_device_ms_total(const tts_ctx *c) { return c ? c->total_ms : 0.0; }
 int tts_bench_gemv(tts_ctx *c, int32_t op, int32_t B, int32_t iters, float *ms, double *bytes) {
   TTS_API_BODY(c, if (!ms || !bytes || iters < 1) throw tts::ArgError("bad argument"); tts::ar_bench_gemv(c, op, B, iters, ms, bytes))
+}
+
+int tts_bench_decode_step(tts_ctx *c, int32_t iters, float *ms, double *bytes) {
+  TTS_API_BODY(c, if (!ms || !bytes) throw tts::ArgError("bad argument"); tts::ar_bench_step(c, iters, ms, bytes))
 }
 
 }  // extern "C"
