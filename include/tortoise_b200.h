@@ -137,6 +137,11 @@ int tts_bench_gemv(tts_ctx *ctx, int32_t op, int32_t B, int32_t iters, float *ms
  * (streamed weights + KV read/append + embeddings + logits). */
 int tts_bench_decode_step(tts_ctx *ctx, int32_t iters, float *ms_per_step, double *bytes_per_step);
 
+/* micro-benchmark of the streaming mechanism (148 CTAs, disjoint contiguous HBM slices):
+ * mode 0 = ring of TMA bulk copies (stage_bytes x stages), mode 1 = plain LDG.128 loads. */
+int tts_bench_stream(tts_ctx *ctx, int32_t mode, int32_t stage_bytes, int32_t stages, int64_t bytes_per_cta,
+                     int32_t iters, float *ms_per_launch, double *bytes_per_launch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@
 //     per-op path become phases separated by a device-wide barrier (release/acquire atomics
 //     in global memory), so a phase boundary costs ~1 us instead of a kernel boundary;
 //   * every CTA owns a fixed row slice of every weight matrix; thread 0 streams those slices,
-//     in the order the step consumes them, through ONE shared-memory ring (12 x 16 KB) with
+//     in the order the step consumes them, through ONE shared-memory ring (6 x 16 KB) with
 //     1-D TMA bulk copies.  The ring is independent of the phase structure: while the grid
 //     waits at a barrier, the next phases' weights are already landing in shared memory, so
 //     HBM keeps streaming across the dependency stalls;
@@ -19,7 +19,7 @@
 
 namespace tts {
 
-constexpr int MG_STAGES = 12;
+constexpr int MG_STAGES = 6;
 constexpr int MG_CONSUMERS = 256;            // 8 consumer warps
 constexpr int MG_THREADS = MG_CONSUMERS + 32;  // + 1 dedicated weight-stream producer warp
 

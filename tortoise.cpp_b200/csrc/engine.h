@@ -104,6 +104,8 @@ void ar_latents(tts_ctx *c, const int32_t *text, int T, const float *voice, cons
 void ar_bench_gemv(tts_ctx *c, int op, int B, int iters, float *ms, double *bytes);
 void ar_bench_step(tts_ctx *c, int iters, float *ms, double *bytes);
 void ar_free(tts_ctx *c);
+void bench_stream(tts_ctx *c, int mode, int stage_bytes, int stages, size_t bytes_per_cta, int iters, float *ms,
+                  double *bytes);
 // implemented in diffusion.cu / vocoder.cu
 void diff_load(tts_ctx *c, const char *path);
 void diff_eps(tts_ctx *c, const float *latents, int L, const float *x, int S, int timestep, int cond_free,

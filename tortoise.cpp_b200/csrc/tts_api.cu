@@ -154,4 +154,11 @@ int tts_bench_decode_step(tts_ctx *c, int32_t iters, float *ms, double *bytes) {
   TTS_API_BODY(c, if (!ms || !bytes) throw tts::ArgError("bad argument"); tts::ar_bench_step(c, iters, ms, bytes))
 }
 
+int tts_bench_stream(tts_ctx *c, int32_t mode, int32_t stage_bytes, int32_t stages, int64_t bytes_per_cta, int32_t iters,
+                     float *ms, double *bytes) {
+  TTS_API_BODY(c, if (!ms || !bytes || stage_bytes % 16 || stages < 1 || bytes_per_cta % stage_bytes || size_t(stages) * stage_bytes > 200 * 1024)
+                      throw tts::ArgError("bad argument");
+               tts::bench_stream(c, mode, stage_bytes, stages, size_t(bytes_per_cta), iters, ms, bytes))
+}
+
 }  // extern "C"
