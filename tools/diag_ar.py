@@ -1,5 +1,5 @@
 import os, sys, numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _pkg
 pkg = _pkg.import_pkg(); sw = _pkg.import_sub("synth_weights"); hl=_pkg.import_sub("host").HostLib()
 md = os.environ.get("TTS_MODEL_DIR", "/tmp/tortoise_b200_models"); sw.generate(md)

@@ -1,6 +1,6 @@
 # quick AR timing probe (dev tool; bench.py is the contract)
 import os, sys, time, numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _pkg
 pkg = _pkg.import_pkg(); sw = _pkg.import_sub("synth_weights")
 md = os.environ.get("TTS_MODEL_DIR", "/tmp/tortoise_b200_models"); sw.generate(md)

@@ -1,5 +1,5 @@
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _pkg
 pkg = _pkg.import_pkg()
 eng = pkg.Engine(dtype=pkg.DTYPE_F16, max_batch=1, max_positions=64)
