@@ -60,7 +60,8 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x));
 static __global__ void __launch_bounds__(256) gn_apply_kernel(const float *X, const float *stats, const float *w,
                                                        const float *b, const float *ss, __half *out16,
                                                        float *out32, int T, int halo, int ldo, int silu,
-                                                       const int *step_ptr, int ss_step_stride) {
+                                                       const int *step_ptr, int ss_step_stride,
+                                                       const double *partial, int mtiles) {
   pdl_launch_dependents();
   pdl_wait();
   // the per-timestep scale|shift table advances with a device-side step counter so that one
@@ -73,7 +74,23 @@ static __global__ void __launch_bounds__(256) gn_apply_kernel(const float *X, co
   if (t >= 0 && t < T) {
     const float4 x = *reinterpret_cast<const float4 *>(X + (size_t(seq) * T + t) * kDim + c);
     const int g = c >> 5;
-    const float mean = stats[(seq * 32 + g) * 2], rstd = stats[(seq * 32 + g) * 2 + 1];
+    float mean, rstd;
+    if (partial) {
+      // statistics fused into the producing GEMM's epilogue: {sum, sumsq} per M tile, in double
+      double s1 = 0.0, s2 = 0.0;
+      for (int i = 0; i < mtiles; ++i) {
+        s1 += partial[((size_t(seq) * 32 + g) * mtiles + i) * 2];
+        s2 += partial[((size_t(seq) * 32 + g) * mtiles + i) * 2 + 1];
+      }
+      const double n = double(T) * 32.0, md = s1 / n;
+      mean = float(md);
+      double var = s2 / n - 2.0 * md * double(mean) + double(mean) * double(mean);  // E[(x - mean_f)^2]
+      if (var < 0.0) var = 0.0;
+      rstd = 1.0f / sqrtf(float(var) + 1e-6f);
+    } else {
+      mean = stats[(seq * 32 + g) * 2];
+      rstd = stats[(seq * 32 + g) * 2 + 1];
+    }
     const float4 w4 = *reinterpret_cast<const float4 *>(w + c);
     const float4 b4 = *reinterpret_cast<const float4 *>(b + c);
     v[0] = (x.x - mean) * rstd * w4.x + b4.x;

@@ -50,6 +50,9 @@ struct DiffModel {
   int graph_S = -1;
   size_t noise_cap = 0;
   int run_S = 0, run_steps = 0, run_i = -1;  // streaming sampler state
+  double *gn_partial = nullptr;    // fused GroupNorm statistics written by the last GEMM epilogue
+  const float *partial_src = nullptr;  // ... and the tensor they describe (null = stale)
+  int partial_mtiles = 0;
   float *h_pin = nullptr;  // pinned staging for x / outputs
   size_t h_pin_bytes = 0;
   // cached conditioning
@@ -207,6 +210,8 @@ static void ensure_buffers(tts_ctx *c, int S, int steps) {
     grow(&m.rpb, size_t(S) + 8);
     grow(&m.up_idx, size_t(S));
     if (!m.d_step) TTS_CUDA_TRY(cudaMalloc(&m.d_step, 4));
+    if (!m.gn_partial) TTS_CUDA_TRY(cudaMalloc(&m.gn_partial, size_t(2) * 32 * 64 * 2 * sizeof(double)));
+    m.partial_src = nullptr;  // buffers moved: no tensor has fused statistics
     if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; m.graph_S = -1; }
     m.capS = S;
     m.cond_L = m.cond_S = -1;
@@ -227,9 +232,15 @@ static void ensure_buffers(tts_ctx *c, int S, int steps) {
 static void tg(tts_ctx *c, const Launcher &L, const __half *Ahi, const __half *Alo, const __half *Whi, const __half *Wlo,
                const float *bias, float *C, int M, int N, int K, int lda, int ldc, int epi, int taps = 1, int T = 0,
                int halo = 0) {
-  TGemmArgs g{Ahi, Alo, Whi, Wlo, bias, C, nullptr, nullptr, M, N, K, lda, ldc, 0, epi, taps, 1, taps / 2, halo,
-              T > 0 ? T : M};
-  launch_gemm(L, g);
+  DiffModel &m = *c->diff;
+  const int Tt = T > 0 ? T : M;
+  TGemmArgs g{Ahi, Alo, Whi, Wlo, bias, C, nullptr, nullptr, M, N, K, lda, ldc, 0, epi, taps, 1, taps / 2, halo, Tt};
+  // outputs that feed a GroupNorm (x, h1, code embedding): let the epilogue produce the statistics
+  const bool gn_target = T > 0 && N == kDim && (C == m.X || C == m.CW || C == m.H1) && Tt <= 64 * T5_BM;
+  if (gn_target) g.gn_partial = m.gn_partial;
+  const int produced = launch_gemm(L, g);
+  if (produced) { m.partial_src = C; m.partial_mtiles = produced; }
+  else if (C == m.partial_src) m.partial_src = nullptr;
 }
 
 // f16 x f16 -> f32 convolution over nseq sequences of T frames (halo 1)
@@ -241,9 +252,11 @@ static void conv(tts_ctx *c, const Launcher &L, const __half *X16, const __half 
 static void gn(tts_ctx *c, const Launcher &L, const float *X, const float *w, const float *b, const float *ss,
                __half *out16, float *out32, int nseq, int T, int silu) {
   DiffModel &m = *c->diff;
-  L(gn_stats_kernel, dim3(32, nseq), dim3(256), 0, X, m.stats, T);
+  const bool fused = m.partial_src == X;
+  if (out32 && out32 == m.partial_src) m.partial_src = nullptr;  // about to be overwritten
+  if (!fused) L(gn_stats_kernel, dim3(32, nseq), dim3(256), 0, X, m.stats, T);
   L(gn_apply_kernel, dim3(T + 2, nseq), dim3(256), 0, X, (const float *)m.stats, w, b, ss, out16, out32, T, 1, kDim,
-    silu, (const int *)m.d_step, 16 * 2048);
+    silu, (const int *)m.d_step, 16 * 2048, (const double *)(fused ? m.gn_partial : nullptr), m.partial_mtiles);
 }
 
 // ResBlock (main.cpp:3347-3480): x += conv3(silu((GN(h)w+b)(1+scale)+shift)),
@@ -263,7 +276,8 @@ static void attn_block(tts_ctx *c, const Launcher &L, const DAttn &a, float *x, 
   conv(c, L, m.A16, a.w_qkv, a.b_qkv, m.QKV, nseq, T, kDim, 3072, 1, 3072, E_BIAS);
   L(diff_attn_kernel, dim3((T + 15) / 16, kHeads, nseq), dim3(128), 0, (const float *)m.QKV,
     (const float *)a.relbias, (const int *)m.rpb, m.ATThi, m.ATTlo, T);
-  tg(c, L, m.ATThi, m.ATTlo, a.proj_hi, a.proj_lo, a.b_proj, x, nseq * T, kDim, kDim, kDim, kDim, E_BIAS_RESID);
+  tg(c, L, m.ATThi, m.ATTlo, a.proj_hi, a.proj_lo, a.b_proj, x, nseq * T, kDim, kDim, kDim, kDim, E_BIAS_RESID,
+     1, T, 0);  // per-sequence M tiles so the fused GroupNorm statistics stay per sequence
 }
 
 // timestep-invariant conditioning branch -> CE[0] (conditioned, stretched to S), CE[1]
@@ -356,6 +370,7 @@ void diff_eps(tts_ctx *c, const float *latents, int Lf, const float *x, int S, i
   TTS_CUDA_TRY(cudaMemcpyAsync(m.x_dev, x, size_t(100) * S * 4, cudaMemcpyHostToDevice, c->stream));
   TTS_CUDA_TRY(cudaMemcpyAsync(m.CW, m.CE + (cond_free ? size_t(S) * kDim : 0), size_t(S) * kDim * 4,
                                cudaMemcpyDeviceToDevice, c->stream));
+  m.partial_src = nullptr;
   run_denoiser(c, L, 1, S, m.EMB);
   // OUT is time-major [S][200]; the C-ABI returns the reference's [200][S]
   float *h = pin(c, size_t(S) * 200 * 4);
@@ -424,6 +439,7 @@ void diff_step(tts_ctx *c, const float *noise_block) {
   // step is captured once into a CUDA graph and replayed n_steps times.
   auto enqueue_step = [&](const Launcher &LL) {
     TTS_CUDA_TRY(cudaMemcpyAsync(m.CW, m.CE, size_t(2) * S * kDim * 4, cudaMemcpyDeviceToDevice, c->stream));
+    m.partial_src = nullptr;  // CW was overwritten by a copy: its fused statistics are stale
     run_denoiser(c, LL, 2, S, m.EMB);
     LL(ddpm_step_kernel, dim3(std::min(148, int((nx + 255) / 256))), dim3(256), 0, m.x_dev, (const float *)m.OUT,
        (const float *)m.noise_dev, (const DdpmCoef *)m.coefs, (const int *)m.d_step, S);

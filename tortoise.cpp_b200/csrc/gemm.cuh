@@ -172,6 +172,10 @@ struct TGemmArgs {
   // A row seq*(T+2*halo) + t + halo + tap*dil - pad; W is [taps][N][K].  Plain GEMM: taps = 1,
   // T = M, halo = pad = 0.
   int taps, dil, pad, halo, T;
+  // optional fused GroupNorm statistics of the OUTPUT (tcgen05 path, BN = 32 = one 32-channel
+  // group per N tile): per (sequence, group, M tile) {sum, sum of squares} in double.
+  double *gn_partial;
+  int gn_mtiles;
 };
 
 constexpr int TG_BM = 64, TG_BN = 64, TG_BK = 32, TG_LD = TG_BK + 8, TG_STAGES = 3;

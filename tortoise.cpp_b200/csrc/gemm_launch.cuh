@@ -4,7 +4,7 @@
 #pragma once
 #include <stdlib.h>
 
-#include "tc5gemm.cuh"
+#include "tc5v2.cuh"
 
 namespace tts {
 
@@ -17,13 +17,29 @@ static inline bool tc5_enabled() {
   return v == 1;
 }
 
-static inline void launch_gemm(const Launcher &L, const TGemmArgs &g) {
+static inline bool tc5_v1_forced() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("TTS_TC5_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// returns the number of partial entries per (sequence, group) when the fused GroupNorm
+// statistics (g.gn_partial) were produced, 0 otherwise
+static inline int launch_gemm(const Launcher &L, const TGemmArgs &g_in) {
+  TGemmArgs g = g_in;
+  if (tc5_enabled() && !tc5_v1_forced() && tc5v2_supported(g)) return launch_tc5v2(L, g);
   if (tc5_enabled() && g.K % T5_BK == 0) {
     const bool alo = g.Alo != nullptr, wlo = g.Wlo != nullptr;
     const int nseq = g.M / g.T;                      // M = nseq * T always
     const int mt = (g.T + T5_BM - 1) / T5_BM;        // tiles per sequence
     // BN = 64 halves the A re-reads; BN = 32 doubles the CTA count when the grid would be small
-    const bool bn64 = ((g.N + 63) / 64) * mt * nseq >= 120;  // measured: BN = 32 (more CTAs) wins for N = 1024
+    const bool want_gn = g.gn_partial != nullptr && g.N == 1024;
+    if (!want_gn) g.gn_partial = nullptr;
+    g.gn_mtiles = mt;
+    const bool bn64 = !want_gn && ((g.N + 63) / 64) * mt * nseq >= 120;  // measured: BN = 32 (more CTAs) wins for N = 1024
     // deep pipeline (8 x 20-24 KB stages) for single-plane operands (the convolutions): these
     // GEMMs are small (M = 2S ~ 400 rows) and latency-bound; 4 stages when lo planes double a stage
     const bool deep = !alo && !wlo;
@@ -41,7 +57,7 @@ static inline void launch_gemm(const Launcher &L, const TGemmArgs &g) {
       if (deep) go(tc5gemm_kernel<32, 8>, 32, 8);
       else go(tc5gemm_kernel<32, 4>, 32, 4);
     }
-    return;
+    return want_gn ? mt : 0;
   }
   static bool attr_done = false;
   if (!attr_done) {
@@ -51,6 +67,7 @@ static inline void launch_gemm(const Launcher &L, const TGemmArgs &g) {
   }
   dim3 grid((g.N + TG_BN - 1) / TG_BN, (g.M + TG_BM - 1) / TG_BM);
   L(tgemm_kernel, grid, dim3(128), tgemm_smem_bytes(), g);
+  return 0;
 }
 
 }  // namespace tts

@@ -167,6 +167,7 @@ static __global__ void __launch_bounds__(T5_THREADS) tc5gemm_kernel(TGemmArgs g)
     mbar_wait(done, 0);
     tc5_fence_after();
     const int q = warp & 3;
+    double gs1 = 0.0, gs2 = 0.0;  // fused GroupNorm statistics of this thread's output row
     const int row_in_tile = q * 32 + lane;  // TMEM lane == tile row
     const int m = m0 + row_in_tile;
 #pragma unroll
@@ -190,6 +191,8 @@ static __global__ void __launch_bounds__(T5_THREADS) tc5gemm_kernel(TGemmArgs g)
             r4.z = apply_epi(g.epi, v[j + 2], b4.z, o4.z);
             r4.w = apply_epi(g.epi, v[j + 3], b4.w, o4.w);
             if (g.C) *reinterpret_cast<float4 *>(g.C + size_t(m) * g.ldc + n) = r4;
+            gs1 += (double(r4.x) + double(r4.y)) + (double(r4.z) + double(r4.w));
+            gs2 += (double(r4.x) * r4.x + double(r4.y) * r4.y) + (double(r4.z) * r4.z + double(r4.w) * r4.w);
             if (g.Chi) {
               const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
@@ -214,6 +217,19 @@ static __global__ void __launch_bounds__(T5_THREADS) tc5gemm_kernel(TGemmArgs g)
             }
           }
         }
+      }
+    }
+    if (BN == 32 && g.gn_partial && warp < 4) {
+      // one N tile == one GroupNorm group (32 channels): reduce {sum, sumsq} over the tile rows
+      double *gred = reinterpret_cast<double *>(tmem_slot + 2);
+      gs1 = warp_sum_d(gs1);
+      gs2 = warp_sum_d(gs2);
+      if (lane == 0) { gred[warp * 2] = gs1; gred[warp * 2 + 1] = gs2; }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (tid == 0) {
+        double *o = g.gn_partial + ((size_t(seq) * 32 + blockIdx.x) * g.gn_mtiles + blockIdx.y) * 2;
+        o[0] = (gred[0] + gred[2]) + (gred[4] + gred[6]);
+        o[1] = (gred[1] + gred[3]) + (gred[5] + gred[7]);
       }
     }
   } else if (lane == 0) {

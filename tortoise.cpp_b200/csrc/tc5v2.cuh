@@ -1,0 +1,392 @@
+// tc5v2.cuh -- tcgen05 GEMM / implicit conv, second generation: TMA tensor-map loads,
+// 128 x 128 output tiles and split-K across a thread-block cluster.
+//
+// Same contract as tc5gemm_kernel / tgemm_kernel (gemm.cuh: C = (Ahi+Alo) x (Whi+Wlo)^T over
+// `taps` shifted K passes, f32 accumulation in TMEM, fused epilogue).  What changed, and why:
+//   * the first-generation kernel (128 x 32 tiles, cp.async loaders) re-read every A tile from
+//     32 CTAs at once: ~120 MB of L2->SM traffic per 3-tap convolution, served at ~3 TB/s
+//     (profiles/r01_tc5_ncu_full.md) -- 4x under both the L2 and the per-SM LSU limits, i.e.
+//     bound by the same few L2 lines being hammered by every CTA.  128 x 128 tiles cut the
+//     traffic 2.5x; the lost parallelism (32 tiles for the [382 x 1024] problems of the
+//     denoiser) comes back as split-K: `csz` CTAs of one cluster (1,1,csz) each accumulate a
+//     K slice of the SAME output tile in their own TMEM, so concurrent CTAs pull DIFFERENT
+//     bytes;
+//   * operands arrive through TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B boxes of 64 halves x
+//     128 rows) issued by ONE thread -- no per-lane address math, no LDGSTS issue limit;
+//     the weight boxes of the first pipeline stages are requested BEFORE griddepcontrol.wait
+//     (weights never depend on the previous kernel), activations after;
+//   * split-K reduction is deterministic: every CTA parks its f32 partial tile in its own
+//     shared memory (row-major, padded), the cluster synchronises, and CTA r sums rows
+//     [r * 128 / csz, (r + 1) * 128 / csz) over ranks 0..csz-1 through distributed shared
+//     memory in fixed order, then runs the epilogue with fully coalesced 512-byte row stores;
+//   * GroupNorm statistics of the output (one 128-column tile = 4 groups) are reduced in the
+//     same epilogue in double, per (sequence, group, M tile, cluster rank) in fixed order.
+// warps 0-7: TMEM -> smem dump, reduction, epilogue; warp 8 lane 0: tcgen05.mma issuer;
+// warp 9 lane 0: TMA producer.
+#pragma once
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "tc5gemm.cuh"
+
+namespace tts {
+
+constexpr int T6_BM = 128, T6_BN = 128, T6_BK = 64;
+constexpr int T6_MMA_WARP = 8, T6_PROD_WARP = 9, T6_THREADS = 10 * 32;
+constexpr int T6_PLANE = 128 * 128;        // bytes of one 128-row x 64-half swizzled box
+constexpr int T6_RED_LD = T6_BN + 4;       // padded row of the f32 partial tile (conflict-free both ways)
+constexpr int T6_CTRL = 1024;              // barriers + tmem slot + GN scratch
+constexpr int T6_MAX_STAGES = 8;
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(ra)
+               : "memory");
+  return v;
+}
+
+static __global__ void __launch_bounds__(T6_THREADS, 1)
+    tc5v2_kernel(TGemmArgs g, const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
+                 const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, int csz,
+                 int stages) {
+  extern __shared__ unsigned char t6_raw[];
+  unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(t6_raw) + 1023) & ~uintptr_t(1023));
+  const bool has_alo = g.Alo != nullptr, has_wlo = g.Wlo != nullptr;
+  const uint32_t a_planes = has_alo ? 2 : 1, w_planes = has_wlo ? 2 : 1;
+  const uint32_t stage_bytes = T6_PLANE * (a_planes + w_planes);
+  // the ring doubles as the f32 partial tile after the MMAs: at least 128 x 132 x 4 = 66 KB
+  const size_t ring_bytes = max(size_t(stages) * stage_bytes, size_t(T6_BM) * T6_RED_LD * 4);
+  unsigned char *ctrl = base + ring_bytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(ctrl);
+  uint64_t *empty = full + T6_MAX_STAGES;
+  uint64_t *done = empty + T6_MAX_STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+  double *gw = reinterpret_cast<double *>(ctrl + 256);  // [8 warps][4 groups][2]
+  float *red = reinterpret_cast<float *>(base);         // partial tile, reuses the stage ring after the MMAs
+
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int rank = blockIdx.z % csz, seq = blockIdx.z / csz;
+  const int t0 = blockIdx.y * T6_BM;
+  const int rows_valid = min(T6_BM, g.T - t0);
+  const int m0 = seq * g.T + t0, n0 = blockIdx.x * T6_BN;
+  const int kchunks = g.K / T6_BK;
+  const int iters = g.taps * kchunks;
+  const int it0 = int(int64_t(iters) * rank / csz), it1 = int(int64_t(iters) * (rank + 1) / csz);
+  const int nit = it1 - it0;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);   // producer's arrive.expect_tx; the TMA engine completes the bytes
+      mbar_init(&empty[s], 1);  // tcgen05.commit
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == T6_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(uint32_t(T6_BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc5_fence_before();
+  __syncthreads();
+  tc5_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  pdl_launch_dependents();
+
+  if (warp == T6_PROD_WARP) {
+    if (lane == 0) {
+      // ================= TMA producer (one thread) =================
+      const int a_row0 = seq * (g.T + 2 * g.halo) + t0 + g.halo - g.pad;
+      auto load_w = [&](int j) {
+        const int it = it0 + j, s = j % stages;
+        const int tap = it / kchunks, k0 = (it % kchunks) * T6_BK;
+        unsigned char *sp = base + size_t(s) * stage_bytes + T6_PLANE * a_planes;
+        tma_load_2d(sp, &mWhi, k0, tap * g.N + n0, &full[s]);
+        if (has_wlo) tma_load_2d(sp + T6_PLANE, &mWlo, k0, tap * g.N + n0, &full[s]);
+      };
+      auto load_a = [&](int j) {
+        const int it = it0 + j, s = j % stages;
+        const int tap = it / kchunks, k0 = (it % kchunks) * T6_BK;
+        unsigned char *sp = base + size_t(s) * stage_bytes;
+        tma_load_2d(sp, &mAhi, k0, a_row0 + tap * g.dil, &full[s]);
+        if (has_alo) tma_load_2d(sp + T6_PLANE, &mAlo, k0, a_row0 + tap * g.dil, &full[s]);
+      };
+      const int pre = min(stages, nit);
+      for (int j = 0; j < pre; ++j) {  // weights first: they do not depend on the previous kernel
+        mbar_arrive_expect_tx(&full[j], stage_bytes);
+        load_w(j);
+      }
+      pdl_wait();
+      for (int j = 0; j < pre; ++j) load_a(j);
+      for (int j = pre; j < nit; ++j) {
+        const int s = j % stages;
+        mbar_wait(&empty[s], ((j / stages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], stage_bytes);
+        load_w(j);
+        load_a(j);
+      }
+    }
+  } else if (warp == T6_MMA_WARP) {
+    if (lane == 0) {
+      // ================= MMA issuer (one thread) =================
+      const uint32_t idesc = (1u << 4) | (uint32_t(T6_BN >> 3) << 17) | (uint32_t(T6_BM >> 4) << 24);
+      uint32_t acc = 0;
+      for (int j = 0; j < nit; ++j) {
+        const int s = j % stages;
+        mbar_wait(&full[s], (j / stages) & 1);
+        tc5_fence_after();
+        const uint32_t sa = smem_u32(base + size_t(s) * stage_bytes);
+        const uint32_t sa_lo = sa + T6_PLANE;
+        const uint32_t sw = sa + T6_PLANE * a_planes;
+        const uint32_t sw_lo = sw + T6_PLANE;
+#pragma unroll
+        for (int k = 0; k < T6_BK / 16; ++k) {
+          const uint32_t koff = k * 32;
+          if (has_wlo) { umma_f16(tmem_d, umma_desc_sw128(sa + koff), umma_desc_sw128(sw_lo + koff), idesc, acc); acc = 1; }
+          if (has_alo) { umma_f16(tmem_d, umma_desc_sw128(sa_lo + koff), umma_desc_sw128(sw + koff), idesc, acc); acc = 1; }
+          umma_f16(tmem_d, umma_desc_sw128(sa + koff), umma_desc_sw128(sw + koff), idesc, acc);
+          acc = 1;
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(done);
+    }
+  } else {
+    // ================= TMEM -> shared partial tile =================
+    pdl_wait();  // the epilogue below reads / overwrites C
+    mbar_wait(done, 0);
+    tc5_fence_after();
+    const int q = warp & 3, h = warp >> 2;  // TMEM lane quadrant, 64-column half
+    const int r = q * 32 + lane;
+#pragma unroll
+    for (int cb = 0; cb < 64; cb += 32) {
+      float v[32];
+      tmem_ld32(tmem_d + (uint32_t(q * 32) << 16) + h * 64 + cb, v);
+      float *dst = red + size_t(r) * T6_RED_LD + h * 64 + cb;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  __syncwarp();
+  tc5_fence_before();
+  if (csz > 1) cluster_sync_all();
+  else __syncthreads();
+
+  if (warp < 8) {
+    // ================= split-K reduction + epilogue: rank r owns rows [r, r+1) * 128 / csz =================
+    const int rows_per = T6_BM / csz, row_base = rank * rows_per;
+    const int c = lane * 4, n = n0 + c;
+    const bool vec = (n + 3 < g.N) && (g.ldc % 4 == 0) && (!g.Chi || g.ldh % 4 == 0);
+    float bias[4] = {0.f, 0.f, 0.f, 0.f};
+    if (g.bias) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (n + e < g.N) bias[e] = g.bias[n + e];
+    }
+    const bool resid = g.epi == E_BIAS_RESID || g.epi == E_BIAS_LRELU_RESID;
+    const uint32_t red_u32 = smem_u32(red);
+    double gs1 = 0.0, gs2 = 0.0;
+    for (int rr = warp; rr < rows_per; rr += 8) {
+      const int r = row_base + rr;
+      if (r >= rows_valid) break;
+      const uint32_t off = uint32_t(r * T6_RED_LD + c) * 4;
+      float4 a4;
+      if (csz == 1) {
+        a4 = *reinterpret_cast<const float4 *>(red + size_t(r) * T6_RED_LD + c);
+      } else {
+        a4 = ld_dsmem_f4(red_u32 + off, 0);
+        for (int k = 1; k < csz; ++k) {
+          const float4 p = ld_dsmem_f4(red_u32 + off, k);
+          a4.x += p.x; a4.y += p.y; a4.z += p.z; a4.w += p.w;
+        }
+      }
+      const int m = m0 + r;
+      float acc[4] = {a4.x, a4.y, a4.z, a4.w}, out[4];
+      if (vec) {
+        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (resid) o4 = *reinterpret_cast<const float4 *>(g.C + size_t(m) * g.ldc + n);
+        const float old[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[e] = apply_epi(g.epi, acc[e], bias[e], old[e]);
+        if (g.C) *reinterpret_cast<float4 *>(g.C + size_t(m) * g.ldc + n) = make_float4(out[0], out[1], out[2], out[3]);
+        if (g.Chi) {
+          __half hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hi[e] = __float2half_rn(out[e]);
+            lo[e] = __float2half_rn(out[e] - __half2float(hi[e]));
+          }
+          *reinterpret_cast<uint2 *>(g.Chi + size_t(m) * g.ldh + n) = *reinterpret_cast<uint2 *>(hi);
+          if (g.Clo) *reinterpret_cast<uint2 *>(g.Clo + size_t(m) * g.ldh + n) = *reinterpret_cast<uint2 *>(lo);
+        }
+        gs1 += (double(out[0]) + double(out[1])) + (double(out[2]) + double(out[3]));
+        gs2 += (double(out[0]) * out[0] + double(out[1]) * out[1]) + (double(out[2]) * out[2] + double(out[3]) * out[3]);
+      } else {
+        for (int e = 0; e < 4 && n + e < g.N; ++e) {
+          float old = 0.f;
+          if (resid) old = g.C[size_t(m) * g.ldc + n + e];
+          const float o = apply_epi(g.epi, acc[e], bias[e], old);
+          if (g.C) g.C[size_t(m) * g.ldc + n + e] = o;
+          if (g.Chi) {
+            const __half hi = __float2half_rn(o);
+            g.Chi[size_t(m) * g.ldh + n + e] = hi;
+            if (g.Clo) g.Clo[size_t(m) * g.ldh + n + e] = __float2half_rn(o - __half2float(hi));
+          }
+        }
+      }
+    }
+    if (g.gn_partial) {
+      // lanes 8 i .. 8 i + 7 hold the 32 columns of GroupNorm group n0 / 32 + i
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        gs1 += __shfl_xor_sync(0xffffffffu, gs1, o);
+        gs2 += __shfl_xor_sync(0xffffffffu, gs2, o);
+      }
+      if ((lane & 7) == 0) {
+        gw[(warp * 4 + (lane >> 3)) * 2] = gs1;
+        gw[(warp * 4 + (lane >> 3)) * 2 + 1] = gs2;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < 4) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int w = 0; w < 8; ++w) {
+          s1 += gw[(w * 4 + tid) * 2];
+          s2 += gw[(w * 4 + tid) * 2 + 1];
+        }
+        double *o = g.gn_partial + ((size_t(seq) * 32 + (n0 >> 5) + tid) * g.gn_mtiles + blockIdx.y * csz + rank) * 2;
+        o[0] = s1;
+        o[1] = s2;
+      }
+    }
+  }
+  __syncwarp();
+  if (csz > 1) cluster_sync_all();  // peers have finished reading this CTA's partial tile
+  else __syncthreads();
+  if (warp == T6_MMA_WARP) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(uint32_t(T6_BN)) : "memory");
+  }
+}
+
+// ---- host side: tensor maps (driver entry point fetched through the runtime; no -lcuda) ----
+typedef CUresult (*tts_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static inline tts_encode_tiled_fn tc5v2_encoder() {
+  static tts_encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    TTS_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) throw CudaError("cuTensorMapEncodeTiled is not available in this driver");
+    fn = reinterpret_cast<tts_encode_tiled_fn>(p);
+  }
+  return fn;
+}
+
+// [rows][cols] f16, row pitch ld elements; box = 64 columns x 128 rows, SWIZZLE_128B, OOB -> 0
+static inline CUtensorMap tc5v2_map(const __half *ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+  typedef std::tuple<const void *, uint64_t, uint64_t, uint64_t> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  const Key key(ptr, rows, cols, ld);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * 2};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t es[2] = {1, 1};
+  const CUresult r = tc5v2_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half *>(ptr), dims, strides,
+                                     box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[160];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d) for [%llu x %llu] ld %llu", int(r),
+             (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+    throw CudaError(b);
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  return m;
+}
+
+static inline bool tc5v2_supported(const TGemmArgs &g) {
+  return g.K % T6_BK == 0 && g.lda % 8 == 0 && (reinterpret_cast<uintptr_t>(g.Ahi) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(g.Whi) & 15) == 0 && (!g.Alo || (reinterpret_cast<uintptr_t>(g.Alo) & 15) == 0) &&
+         (!g.Wlo || (reinterpret_cast<uintptr_t>(g.Wlo) & 15) == 0) && g.halo >= g.pad;
+}
+
+// returns the number of per-(sequence, group) partial entries written when GroupNorm statistics
+// were fused (0 = none)
+static inline int launch_tc5v2(const Launcher &L, TGemmArgs g) {
+  const bool alo = g.Alo != nullptr, wlo = g.Wlo != nullptr;
+  const int nseq = g.M / g.T;
+  const int mt = (g.T + T6_BM - 1) / T6_BM, nt = (g.N + T6_BN - 1) / T6_BN;
+  const int iters = g.taps * (g.K / T6_BK);
+  // split-K until the grid covers the 148 SMs once (each rank keeps >= 2 K steps)
+  int csz = 1;
+  while (csz < 8 && nt * mt * nseq * csz * 2 <= 148 && iters >= csz * 4) csz *= 2;
+  const bool want_gn = g.gn_partial != nullptr && g.N % T6_BN == 0 && mt * csz <= 64;
+  if (!want_gn) g.gn_partial = nullptr;
+  g.gn_mtiles = mt * csz;
+  const size_t stage_bytes = size_t(T6_PLANE) * ((alo ? 2 : 1) + (wlo ? 2 : 1));
+  const size_t budget = 226 * 1024 - 1024 - T6_CTRL;
+  int stages = int(budget / stage_bytes);
+  if (stages > T6_MAX_STAGES) stages = T6_MAX_STAGES;
+  const int per_rank = (iters + csz - 1) / csz;
+  if (stages > per_rank) stages = per_rank;
+  size_t smem = stages * stage_bytes;
+  if (smem < size_t(T6_BM) * T6_RED_LD * 4) smem = size_t(T6_BM) * T6_RED_LD * 4;  // partial tile
+  smem += 1024 + T6_CTRL;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TTS_CUDA_TRY(cudaFuncSetAttribute(tc5v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_done = true;
+  }
+  const uint64_t a_rows = uint64_t(nseq) * (g.T + 2 * g.halo);
+  const CUtensorMap mAhi = tc5v2_map(g.Ahi, a_rows, g.K, g.lda);
+  const CUtensorMap mAlo = alo ? tc5v2_map(g.Alo, a_rows, g.K, g.lda) : mAhi;
+  const CUtensorMap mWhi = tc5v2_map(g.Whi, uint64_t(g.taps) * g.N, g.K, g.K);
+  const CUtensorMap mWlo = wlo ? tc5v2_map(g.Wlo, uint64_t(g.taps) * g.N, g.K, g.K) : mWhi;
+
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nt, mt, nseq * csz);
+  cfg.blockDim = dim3(T6_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = L.stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = L.pdl ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 1;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = csz;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  TTS_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc5v2_kernel, g, mAhi, mAlo, mWhi, mWlo, csz, stages));
+  if (L.counter) ++*L.counter;
+  return want_gn ? mt * csz : 0;
+}
+
+}  // namespace tts
