@@ -9,6 +9,7 @@
 #include "gemm_launch.cuh"
 #include "wsgemv.cuh"
 #include "ar_mega.cuh"
+#include "ar_mega2.cuh"
 
 namespace tts {
 
@@ -138,10 +139,22 @@ void ar_load(tts_ctx *c, const char *path) {
     TTS_CUDA_TRY(cudaMalloc(&m.mega_layers, sizeof(MegaLayer) * kLayers));
     TTS_CUDA_TRY(cudaMemcpy(m.mega_layers, ml.data(), sizeof(MegaLayer) * kLayers, cudaMemcpyHostToDevice));
     TTS_CUDA_TRY(cudaMalloc(&m.mega_bar, 2 * sizeof(unsigned int)));
+    {  // exchange buffers of ar_mega2.cuh: zero tags never match (launch generations start at 1)
+      const size_t nb = std::min<size_t>(B, 4);
+      const size_t sizes[5] = {M2_REP * nb * kDim, M2_REP * nb * kDim, nb * 3072, M2_REP * nb * (kFF / 2),
+                               M2_REP * nb * kHeads * M2_SMAX * M2_REC};
+      uint2 **ptrs[5] = {&m.ll_h, &m.ll_h2, &m.ll_qkv, &m.ll_m, &m.ll_att};
+      for (int i = 0; i < 5; ++i) {
+        m.ll_bytes[i] = sizes[i] * sizeof(uint2);
+        TTS_CUDA_TRY(cudaMalloc(ptrs[i], m.ll_bytes[i]));
+        TTS_CUDA_TRY(cudaMemset(*ptrs[i], 0, m.ll_bytes[i]));
+      }
+      m.mega_epoch = 0;
+    }
     const char *tr = getenv("TTS_MEGA_TRACE");
     if (tr && tr[0] == '1') {
-      TTS_CUDA_TRY(cudaMalloc(&m.mega_dbg, 2000 * sizeof(long long)));
-      TTS_CUDA_TRY(cudaMemset(m.mega_dbg, 0, 2000 * sizeof(long long)));
+      TTS_CUDA_TRY(cudaMalloc(&m.mega_dbg, 8000 * sizeof(long long)));
+      TTS_CUDA_TRY(cudaMemset(m.mega_dbg, 0, 8000 * sizeof(long long)));
     }
   }
   m.loaded = true;
@@ -255,6 +268,41 @@ static void launch_mega_t(tts_ctx *c, int B, int n_past, int pos_id) {
     TTS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k, dim3(c->num_sms), dim3(MG_THREADS), args, smem, c->stream));
   }
   c->launches += 1;
+}
+
+// Second generation (ar_mega2.cuh): tag-fused activation exchange, up to 4 candidates per weight stream.
+template <typename WT, int BT>
+static void launch_mega2_bt(tts_ctx *c, Mega2Args &a) {
+  auto k = ar_decode_mega2_kernel<WT, BT>;
+  static bool attr = false;
+  const size_t smem = mega2_smem_bytes<BT>();
+  if (!attr) { TTS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  void *args[] = {&a};
+  TTS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k, dim3(c->num_sms), dim3(M2_THREADS), args, smem, c->stream));
+  c->launches += 1;
+}
+
+template <typename WT>
+static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
+  ArModel &m = c->ar;
+  ArState &s = c->ars;
+  if (m.mega_epoch >= (1u << 24) - 1) {  // tag generations exhausted: start over with clean buffers
+    uint2 *ptrs[5] = {m.ll_h, m.ll_h2, m.ll_qkv, m.ll_m, m.ll_att};
+    for (int i = 0; i < 5; ++i) TTS_CUDA_TRY(cudaMemsetAsync(ptrs[i], 0, m.ll_bytes[i], c->stream));
+    m.mega_epoch = 0;
+  }
+  Mega2Args a{};
+  a.layers = (const MegaLayer *)m.mega_layers;
+  a.lnf_w = m.lnf_w; a.lnf_b = m.lnf_b; a.lm0_w = m.lm0_w; a.lm0_b = m.lm0_b; a.lm_b = m.lm_b; a.lm_w = m.lm_w;
+  a.mel_emb = m.mel_emb; a.mel_pos = m.mel_pos; a.tokens = s.d_tokens;
+  a.ll_h = m.ll_h; a.ll_h2 = m.ll_h2; a.ll_qkv = m.ll_qkv; a.ll_m = m.ll_m; a.ll_att = m.ll_att;
+  a.logits = s.logits; a.kc = s.kc; a.vc = s.vc;
+  a.B = B; a.Bmax = s.Bmax; a.P = s.P; a.n_past = n_past; a.pos_id = pos_id;
+  a.epoch = ++m.mega_epoch;
+  a.dbg = m.mega_dbg;
+  if (B == 1) launch_mega2_bt<WT, 1>(c, a);
+  else if (B == 2) launch_mega2_bt<WT, 2>(c, a);
+  else launch_mega2_bt<WT, 4>(c, a);
 }
 
 static void ensure_rows(tts_ctx *c, size_t rows) {
@@ -385,9 +433,14 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
   TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
   if (c->use_mega && s.P <= 1024) {
     TTS_CUDA_TRY(cudaMemcpyAsync(s.d_tokens, s.h_tokens, B * 4, cudaMemcpyHostToDevice, c->stream));
-    TTS_CUDA_TRY(cudaMemsetAsync(c->ar.mega_bar, 0, 2 * sizeof(unsigned int), c->stream));
-    if (c->ar.dtype == TTS_DTYPE_F16) launch_mega_t<__half>(c, B, s.n_past, pos_id);
-    else launch_mega_t<float>(c, B, s.n_past, pos_id);
+    if (B <= 4 && !c->use_mega_v1) {
+      if (c->ar.dtype == TTS_DTYPE_F16) launch_mega2_t<__half>(c, B, s.n_past, pos_id);
+      else launch_mega2_t<float>(c, B, s.n_past, pos_id);
+    } else {
+      TTS_CUDA_TRY(cudaMemsetAsync(c->ar.mega_bar, 0, 2 * sizeof(unsigned int), c->stream));
+      if (c->ar.dtype == TTS_DTYPE_F16) launch_mega_t<__half>(c, B, s.n_past, pos_id);
+      else launch_mega_t<float>(c, B, s.n_past, pos_id);
+    }
     TTS_CUDA_TRY(cudaMemcpyAsync(s.h_logits, s.logits, size_t(B) * kMelVocab * 4, cudaMemcpyDeviceToHost, c->stream));
   } else if (c->use_graph) {
     if (!s.step_graph || s.step_graph_B != B) build_step_graph(c, B);
@@ -408,9 +461,9 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
   c->total_ms += c->last_ms;
     if (logits_out) memcpy(logits_out, s.h_logits, size_t(B) * kMelVocab * 4);
     if (c->ar.mega_dbg && getenv("TTS_MEGA_TRACE_DUMP")) {
-      std::vector<long long> t(2000);
-      cudaMemcpy(t.data(), c->ar.mega_dbg, 2000 * sizeof(long long), cudaMemcpyDeviceToHost);
-      for (int i = 1; i < 1000 && t[2 * i] != 0; ++i)
+      std::vector<long long> t(8000);
+      cudaMemcpy(t.data(), c->ar.mega_dbg, 8000 * sizeof(long long), cudaMemcpyDeviceToHost);
+      for (int i = 1; i < 4000 && t[2 * i] != 0; ++i)
         fprintf(stderr, "trace %3d tag %2lld dt %6lld\n", i, t[2 * i], t[2 * i + 1] - t[2 * i - 1]);
     }
   }

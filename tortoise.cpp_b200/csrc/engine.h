@@ -46,6 +46,10 @@ struct ArModel {
   void *mega_layers = nullptr;   // device MegaLayer[30] (ar_mega.cuh)
   unsigned int *mega_bar = nullptr;
   long long *mega_dbg = nullptr;  // device trace buffer (TTS_MEGA_TRACE=1)
+  // (value, tag) exchange buffers of the second-generation persistent step (ar_mega2.cuh)
+  uint2 *ll_h = nullptr, *ll_h2 = nullptr, *ll_qkv = nullptr, *ll_m = nullptr, *ll_att = nullptr;
+  size_t ll_bytes[5] = {0, 0, 0, 0, 0};
+  unsigned int mega_epoch = 0;  // launch counter = tag generation
 };
 
 struct ArState {
@@ -84,6 +88,7 @@ struct tts_ctx {
   bool use_graph = true;
   bool use_pdl = true;
   bool use_mega = true;   // persistent single-kernel decode step (TTS_NO_MEGA=1 -> per-op graph path)
+  bool use_mega_v1 = false;  // TTS_MEGA_V1=1: first-generation persistent step (grid barriers), for A/B
   tts::ArModel ar;
   tts::ArState ars;
   tts::DiffModel *diff = nullptr;

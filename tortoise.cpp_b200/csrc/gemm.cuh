@@ -176,6 +176,7 @@ struct TGemmArgs {
   // group per N tile): per (sequence, group, M tile) {sum, sum of squares} in double.
   double *gn_partial;
   int gn_mtiles;
+  long long *dbg;  // optional per-launch clock trace (TTS_TC5_TRACE=1), else null
 };
 
 constexpr int TG_BM = 64, TG_BN = 64, TG_BK = 32, TG_LD = TG_BK + 8, TG_STAGES = 3;

@@ -90,6 +90,15 @@ static __global__ void __launch_bounds__(T6_THREADS, 1)
   const int iters = g.taps * kchunks;
   const int it0 = int(int64_t(iters) * rank / csz), it1 = int(int64_t(iters) * (rank + 1) / csz);
   const int nit = it1 - it0;
+  const bool tr = g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  auto trace = [&](int slot) {
+    if (tr) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      g.dbg[slot] = t;
+    }
+  };
+  if (tid == 0) trace(0);
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -110,6 +119,7 @@ static __global__ void __launch_bounds__(T6_THREADS, 1)
   tc5_fence_after();
   const uint32_t tmem_d = *tmem_slot;
   pdl_launch_dependents();
+  if (tid == 0) trace(1);
 
   if (warp == T6_PROD_WARP) {
     if (lane == 0) {
@@ -134,8 +144,11 @@ static __global__ void __launch_bounds__(T6_THREADS, 1)
         mbar_arrive_expect_tx(&full[j], stage_bytes);
         load_w(j);
       }
+      trace(2);
       pdl_wait();
+      trace(3);
       for (int j = 0; j < pre; ++j) load_a(j);
+      trace(4);
       for (int j = pre; j < nit; ++j) {
         const int s = j % stages;
         mbar_wait(&empty[s], ((j / stages) & 1) ^ 1);
@@ -153,6 +166,7 @@ static __global__ void __launch_bounds__(T6_THREADS, 1)
         const int s = j % stages;
         mbar_wait(&full[s], (j / stages) & 1);
         tc5_fence_after();
+        if (j == 0) trace(5);
         const uint32_t sa = smem_u32(base + size_t(s) * stage_bytes);
         const uint32_t sa_lo = sa + T6_PLANE;
         const uint32_t sw = sa + T6_PLANE * a_planes;
@@ -168,12 +182,14 @@ static __global__ void __launch_bounds__(T6_THREADS, 1)
         umma_commit(&empty[s]);
       }
       umma_commit(done);
+      trace(6);
     }
   } else {
     // ================= TMEM -> shared partial tile =================
     pdl_wait();  // the epilogue below reads / overwrites C
     mbar_wait(done, 0);
     tc5_fence_after();
+    if (tid == 0) trace(7);
     const int q = warp & 3, h = warp >> 2;  // TMEM lane quadrant, 64-column half
     const int r = q * 32 + lane;
 #pragma unroll
@@ -187,8 +203,10 @@ static __global__ void __launch_bounds__(T6_THREADS, 1)
   }
   __syncwarp();
   tc5_fence_before();
+  if (tid == 0) trace(8);
   if (csz > 1) cluster_sync_all();
   else __syncthreads();
+  if (tid == 0) trace(9);
 
   if (warp < 8) {
     // ================= split-K reduction + epilogue: rank r owns rows [r, r+1) * 128 / csz =================
@@ -253,6 +271,7 @@ static __global__ void __launch_bounds__(T6_THREADS, 1)
         }
       }
     }
+    if (tid == 0) trace(10);
     if (g.gn_partial) {
       // lanes 8 i .. 8 i + 7 hold the 32 columns of GroupNorm group n0 / 32 + i
 #pragma unroll
@@ -278,8 +297,10 @@ static __global__ void __launch_bounds__(T6_THREADS, 1)
     }
   }
   __syncwarp();
+  if (tid == 0) trace(11);
   if (csz > 1) cluster_sync_all();  // peers have finished reading this CTA's partial tile
   else __syncthreads();
+  if (tid == 0) trace(12);
   if (warp == T6_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(uint32_t(T6_BN)) : "memory");
   }
@@ -384,7 +405,32 @@ static inline int launch_tc5v2(const Launcher &L, TGemmArgs g) {
   attr[1].val.clusterDim.z = csz;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
+  static int trace_mode = -1;
+  static long long *trace_buf = nullptr;
+  if (trace_mode < 0) {
+    const char *e = getenv("TTS_TC5_TRACE");
+    trace_mode = (e && e[0] == '1') ? 1 : 0;
+    if (trace_mode) TTS_CUDA_TRY(cudaMalloc(&trace_buf, 16 * sizeof(long long)));
+  }
+  g.dbg = nullptr;
+  if (trace_mode) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(L.stream, &cs);
+    if (cs == cudaStreamCaptureStatusNone) {
+      TTS_CUDA_TRY(cudaMemsetAsync(trace_buf, 0, 16 * sizeof(long long), L.stream));
+      g.dbg = trace_buf;
+    }
+  }
   TTS_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc5v2_kernel, g, mAhi, mAlo, mWhi, mWlo, csz, stages));
+  if (g.dbg) {
+    long long t[16];
+    TTS_CUDA_TRY(cudaStreamSynchronize(L.stream));
+    TTS_CUDA_TRY(cudaMemcpy(t, trace_buf, sizeof t, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "tc5trace M=%d N=%d K=%d taps=%d grid=(%d,%d,%d) csz=%d stages=%d planes=%d%d :", g.M, g.N, g.K, g.taps, nt, mt,
+            nseq * csz, csz, stages, alo ? 2 : 1, wlo ? 2 : 1);
+    for (int i = 1; i < 13; ++i) fprintf(stderr, " %d:%lld", i, t[i] ? t[i] - t[0] : -1);
+    fprintf(stderr, "\n");
+  }
   if (L.counter) ++*L.counter;
   return want_gn ? mt * csz : 0;
 }

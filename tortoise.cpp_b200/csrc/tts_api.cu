@@ -71,6 +71,7 @@ int tts_init(const tts_config *cfg, tts_ctx **out) {
   c->use_pdl = !(ep && ep[0] == '1');
   const char *em = getenv("TTS_NO_MEGA");
   c->use_mega = !(em && em[0] == '1');
+  { const char *e1 = getenv("TTS_MEGA_V1"); c->use_mega_v1 = e1 && e1[0] == '1'; }
   try {
     TTS_CUDA_TRY(cudaSetDevice(cfg->device));
     TTS_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
