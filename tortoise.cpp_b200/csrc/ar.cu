@@ -152,9 +152,10 @@ void ar_load(tts_ctx *c, const char *path) {
       m.mega_epoch = 0;
     }
     const char *tr = getenv("TTS_MEGA_TRACE");
-    if (tr && tr[0] == '1') {
-      TTS_CUDA_TRY(cudaMalloc(&m.mega_dbg, 8000 * sizeof(long long)));
-      TTS_CUDA_TRY(cudaMemset(m.mega_dbg, 0, 8000 * sizeof(long long)));
+    if (tr && (tr[0] == '1' || tr[0] == '2')) {
+      m.mega_dbg_mode = tr[0] - '0';
+      TTS_CUDA_TRY(cudaMalloc(&m.mega_dbg, kMegaDbgWords * sizeof(long long)));
+      TTS_CUDA_TRY(cudaMemset(m.mega_dbg, 0, kMegaDbgWords * sizeof(long long)));
     }
   }
   m.loaded = true;
@@ -300,6 +301,7 @@ static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
   a.B = B; a.Bmax = s.Bmax; a.P = s.P; a.n_past = n_past; a.pos_id = pos_id;
   a.epoch = ++m.mega_epoch;
   a.dbg = m.mega_dbg;
+  a.dbg_mode = m.mega_dbg_mode;
   if (B == 1) launch_mega2_bt<WT, 1>(c, a);
   else if (B == 2) launch_mega2_bt<WT, 2>(c, a);
   else launch_mega2_bt<WT, 4>(c, a);
@@ -461,10 +463,17 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
   c->total_ms += c->last_ms;
     if (logits_out) memcpy(logits_out, s.h_logits, size_t(B) * kMelVocab * 4);
     if (c->ar.mega_dbg && getenv("TTS_MEGA_TRACE_DUMP")) {
-      std::vector<long long> t(8000);
-      cudaMemcpy(t.data(), c->ar.mega_dbg, 8000 * sizeof(long long), cudaMemcpyDeviceToHost);
-      for (int i = 1; i < 4000 && t[2 * i] != 0; ++i)
-        fprintf(stderr, "trace %3d tag %2lld dt %6lld\n", i, t[2 * i], t[2 * i + 1] - t[2 * i - 1]);
+      std::vector<long long> t(kMegaDbgWords);
+      cudaMemcpy(t.data(), c->ar.mega_dbg, kMegaDbgWords * sizeof(long long), cudaMemcpyDeviceToHost);
+      if (c->ar.mega_dbg_mode == 2) {  // raw [cta][128][4] globaltimer stamps -> file named by the variable
+        if (FILE *f = fopen(getenv("TTS_MEGA_TRACE_DUMP"), "wb")) {
+          fwrite(t.data(), sizeof(long long), size_t(c->num_sms) * 128 * 4, f);
+          fclose(f);
+        }
+      } else {
+        for (int i = 1; i < 4000 && t[2 * i] != 0; ++i)
+          fprintf(stderr, "trace %3d tag %2lld dt %6lld\n", i, t[2 * i], t[2 * i + 1] - t[2 * i - 1]);
+      }
     }
   }
 }

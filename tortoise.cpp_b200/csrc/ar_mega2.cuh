@@ -58,7 +58,8 @@ struct Mega2Args {
   __half *kc, *vc;  // [30][Bmax][16][P][64]
   int B, Bmax, P, n_past, pos_id;
   unsigned int epoch;  // unique per launch (1 .. 2^24-1)
-  long long *dbg;      // optional clock trace of CTA 0 (TTS_MEGA_TRACE=1), else null
+  long long *dbg;      // optional clock trace (TTS_MEGA_TRACE=1: CTA 0, cycle stamps; =2: every CTA, 4 globaltimer stamps per phase)
+  int dbg_mode;
 };
 
 template <int BT>
@@ -91,6 +92,15 @@ __device__ __forceinline__ void cp_async_cg16(void *dst_smem, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Between two polls of a tag that has not arrived.  Measured (tools/xchg_bench.cu): __nanosleep(40)
+// costs ~1800 cycles per call on B200 whatever its argument, i.e. it quantises every exchange to
+// multiples of ~1 us; a plain re-poll (one L2 round trip, ~300 cycles) is the cheapest wait.
+__device__ __forceinline__ void poll_backoff() {}
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <typename WT, int BT>
@@ -173,7 +183,11 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
   // =========================== consumers (256 threads) ========================================
   int dbg_n = 0;
   auto trace = [&](int tag) {
-    if (a.dbg && cta == 0 && tid == 0 && dbg_n < 4000) { a.dbg[2 * dbg_n] = tag; a.dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
+    if (a.dbg && a.dbg_mode == 1 && cta == 0 && tid == 0 && dbg_n < 4000) { a.dbg[2 * dbg_n] = tag; a.dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
+  };
+  // per-CTA phase stamps (mode 2): [cta][phase][4] = phase start, GEMV start, GEMV done, epilogue done
+  auto stamp = [&](int ph, int k) {
+    if (a.dbg && a.dbg_mode == 2 && tid == 0) a.dbg[(size_t(cta) * 128 + ph) * 4 + k] = global_ns();
   };
   const uint32_t tag_base = a.epoch << 8;
   auto tag_of = [&](int layer, int phase) { return tag_base + uint32_t(layer * 8 + phase); };
@@ -186,7 +200,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
   auto poll_unit = [&](const uint2 *p, uint32_t tag) -> float2 {
     uint4 v = ld_ll(p);
     while (v.y != tag || v.w != tag) {
-      __nanosleep(40);
+      poll_backoff();
       v = ld_ll(p);
     }
     return make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
@@ -208,7 +222,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           while (v[b][u].y != tag || v[b][u].w != tag) {
-            __nanosleep(40);
+            poll_backoff();
             v[b][u] = ld_ll(buf + size_t(b) * kDim + u * 512 + 2 * tid);
           }
           hv[b][2 * u] = __uint_as_float(v[b][u].x);
@@ -424,7 +438,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
 #pragma unroll
             for (int u = 0; u < 3; ++u)
               while (v[i][u].y != tg || v[i][u].w != tg) {
-                __nanosleep(40);
+                poll_backoff();
                 v[i][u] = ld_ll(rec + off[u]);
               }
             const float ms = __uint_as_float(v[i][2].x), ls = __uint_as_float(v[i][2].z);
@@ -455,6 +469,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
     const bool tail = ph == kLayers * 4;
     const int li = tail ? kLayers - 1 : (ph >> 2), p = tail ? 0 : (ph & 3);
     const MegaLayer &l = a.layers[li];
+    stamp(ph, 0);
     // ---------------- prologue ----------------
     if (p == 0 || p == 2) {
       if (p == 0 && !tail && cta < n_items) prefetch_kv(li, cta);  // lands while the QKV phase runs
@@ -508,7 +523,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           while (v[u].y != tg || v[u].w != tg) {
-            __nanosleep(40);
+            poll_backoff();
             v[u] = ld_ll(src + 2 * (tid + u * M2_CONSUMERS));
           }
           const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&v[u].x));
@@ -519,6 +534,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
     }
     bar_consumers();
     trace(20 + p);
+    stamp(ph, 1);
 
     // ---------------- GEMV: xin (shared) x this CTA's weight rows (ring) ----------------
     // kind: 0 = QKV (f16 round trip, KV append), 1 = residual, 2 = GELU16, 3 = logits
@@ -619,6 +635,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
       trace(45);
       bar_consumers();
       trace(30 + p);
+      stamp(ph, 2);
       // ---------------- epilogue: one output element per thread ----------------
       const bool act = tid < rows_cta * BT && (tid % BT) < B;
       const int r = tid / BT, b = tid % BT, n = row0 + r;
@@ -656,6 +673,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
         }
       }
     }
+    stamp(ph, 3);
   }
   trace(40);
 }

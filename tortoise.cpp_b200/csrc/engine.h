@@ -35,6 +35,8 @@ struct ArLayer {
   __half *qkv_hi, *qkv_lo, *proj_hi, *proj_lo, *fc_hi, *fc_lo, *proj2_hi, *proj2_lo;
 };
 
+constexpr size_t kMegaDbgWords = 160 * 128 * 4;  // trace buffer of the persistent decode kernels
+
 struct ArModel {
   bool loaded = false;
   int dtype = 0;
@@ -45,7 +47,8 @@ struct ArModel {
   size_t decode_weight_bytes = 0;
   void *mega_layers = nullptr;   // device MegaLayer[30] (ar_mega.cuh)
   unsigned int *mega_bar = nullptr;
-  long long *mega_dbg = nullptr;  // device trace buffer (TTS_MEGA_TRACE=1)
+  long long *mega_dbg = nullptr;  // device trace buffer (TTS_MEGA_TRACE=1|2)
+  int mega_dbg_mode = 0;
   // (value, tag) exchange buffers of the second-generation persistent step (ar_mega2.cuh)
   uint2 *ll_h = nullptr, *ll_h2 = nullptr, *ll_qkv = nullptr, *ll_m = nullptr, *ll_att = nullptr;
   size_t ll_bytes[5] = {0, 0, 0, 0, 0};
