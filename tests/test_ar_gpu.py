@@ -141,6 +141,44 @@ def test_fp16_weight_mode_tracks_oracle(pkg, golden, voice, model_dir):
         eng.close()
 
 
+@pytest.mark.parametrize("B", [1, 2, 4])
+def test_fp16_decode_tensor_core_path_vs_cuda_core_path_and_oracle(pkg, golden, voice, model_dir, B):
+    """f16 weights: the tensor-core persistent step (ar_mega3.cuh, split-f16 activations) against the
+    CUDA-core one (ar_mega2.cuh, TTS_MEGA_V2=1) over a teacher-forced run, and against the oracle."""
+    import _pkg
+    import tortoise_oracle as O
+    sw = _pkg.import_sub("synth_weights")
+    W = sw.read_container(os.path.join(model_dir, "ggml-model.bin"))
+    g = golden("ar_b1.npz")
+    codes = [int(x) for x in g["codes500"][:12]]
+    outs = {}
+    for path in ("v3", "v2"):
+        if path == "v2":
+            os.environ["TTS_MEGA_V2"] = "1"
+        try:
+            eng = pkg.Engine(device=0, dtype=pkg.DTYPE_F16, max_batch=4, max_positions=128)
+        finally:
+            os.environ.pop("TTS_MEGA_V2", None)
+        try:
+            eng.load_ar(os.path.join(model_dir, "ggml-model.bin"))
+            eng.ar_prefill(g["tokens"], voice, B)
+            lgs = []
+            for i, c in enumerate(codes):
+                toks = [(c + 7 * b) % 8192 for b in range(B)]
+                lgs.append(eng.ar_step(toks, i + 2).copy())
+            outs[path] = np.stack(lgs)
+        finally:
+            eng.close()
+    assert np.isfinite(outs["v3"]).all()
+    assert np.abs(outs["v3"] - outs["v2"]).max() < LOGIT_TOL
+    ar = O.AROracle(W, weight_dtype="f16")
+    ar.prefill(g["tokens"], voice, B)
+    for i in range(3):
+        toks = np.array([(codes[i] + 7 * b) % 8192 for b in range(B)])
+        ref = ar.step(toks, i + 2)
+        assert np.abs(outs["v3"][i] - ref).max() < LOGIT_TOL
+
+
 def test_limits_are_errors_not_aborts(engine_f32, golden, voice, pkg):
     g = golden("ar_b1.npz")
     with pytest.raises(pkg.TTSError):

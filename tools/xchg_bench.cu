@@ -38,7 +38,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint4 ld_v4(const void *p) {
+__device__ __forceinline__ uint4 ld_v4_vol(const void *p) {
   uint4 v;
   asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
@@ -48,8 +48,11 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const void *p) {
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+__device__ int g_relaxed;
+__device__ __forceinline__ uint4 ld_v4(const void *p) { return g_relaxed ? ld_relaxed_v4(p) : ld_v4_vol(p); }
 __device__ __forceinline__ void st_v2(void *p, uint32_t a, uint32_t b) {
-  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+  if (g_relaxed) asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+  else asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) {
   uint32_t v;
@@ -80,7 +83,7 @@ struct XArgs {
   uint32_t *counter;  // [REP * 32] (one 128-byte line each)
   const unsigned char *bg;  // background stream source (or null)
   size_t bg_bytes_per_cta;
-  int rep, rounds, mode, sleep_ns, pollwarps, work;
+  int rep, rounds, mode, sleep_ns, pollwarps, work, skew, relaxed, nvec;
   long long *cycles;  // [G]
   float *sink;
 };
@@ -134,15 +137,20 @@ __global__ void __launch_bounds__(NT + 32, 1) xchg_kernel(XArgs a) {
     const int par = r & 1;
     // ---- "work" between exchanges (dependent FMA chain of a.work steps) ----
     float w = S;
-    for (int i = 0; i < a.work; ++i) w = fmaf(w, 1.0000001f, 1e-9f);
+    {
+      // per-(CTA, round) pseudo-random extra work in [0, skew) emulates GEMV finish-time skew
+      int extra = 0;
+      if (a.skew) extra = int((uint32_t(cta * 2654435761u) ^ uint32_t(r * 40503u)) >> 8) % a.skew;
+      for (int i = 0; i < a.work + extra; ++i) w = fmaf(w, 1.0000001f, 1e-9f);
+    }
     // ---- produce ----
-    if (a.mode == 0 || a.mode == 3) {
-      if (tid < rows)
+    if (a.mode == 0 || a.mode == 3 || a.mode == 4) {
+      for (int i = tid; i < rows; i += NT)
         for (int q = 0; q < a.rep; ++q)
-          st_v2(a.ll + (size_t(par) * a.rep + q) * 1024 + row0 + tid, __float_as_uint(w * 1e-3f + float(row0 + tid) * 1e-6f), tag);
+          st_v2(a.ll + (size_t(par) * a.rep + q) * 1024 + row0 + i, __float_as_uint(w * 1e-3f + float(row0 + i) * 1e-6f), tag);
     } else {
-      if (tid < rows)
-        for (int q = 0; q < a.rep; ++q) a.data[(size_t(par) * a.rep + q) * 1024 + row0 + tid] = w * 1e-3f + float(row0 + tid) * 1e-6f;
+      for (int i = tid; i < rows; i += NT)
+        for (int q = 0; q < a.rep; ++q) a.data[(size_t(par) * a.rep + q) * 1024 + row0 + i] = w * 1e-3f + float(row0 + i) * 1e-6f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (a.mode == 1) {
         if (tid < a.rep) {
@@ -163,6 +171,19 @@ __global__ void __launch_bounds__(NT + 32, 1) xchg_kernel(XArgs a) {
       uint4 v0 = ld_v4(buf + 2 * tid), v1 = ld_v4(buf + 512 + 2 * tid);
       while (v0.y != tag || v0.w != tag) { if (a.sleep_ns) __nanosleep(a.sleep_ns); v0 = ld_v4(buf + 2 * tid); }
       while (v1.y != tag || v1.w != tag) { if (a.sleep_ns) __nanosleep(a.sleep_ns); v1 = ld_v4(buf + 512 + 2 * tid); }
+      x[0] = __uint_as_float(v0.x); x[1] = __uint_as_float(v0.z); x[2] = __uint_as_float(v1.x); x[3] = __uint_as_float(v1.z);
+    } else if (a.mode == 4) {
+      const uint2 *buf = a.ll + (size_t(par) * a.rep + rep) * 1024;
+      if (lane == 0) {
+        // sentinel: an element of a producer far away in the grid order
+        const int sidx = ((warp * 131 + cta * 7) & 511) * 2;
+        uint4 sv = ld_v4(buf + sidx);
+        while (sv.y != tag) sv = ld_v4(buf + sidx);
+      }
+      __syncwarp();
+      uint4 v0 = ld_v4(buf + 2 * tid), v1 = ld_v4(buf + 512 + 2 * tid);
+      while (v0.y != tag || v0.w != tag) v0 = ld_v4(buf + 2 * tid);
+      while (v1.y != tag || v1.w != tag) v1 = ld_v4(buf + 512 + 2 * tid);
       x[0] = __uint_as_float(v0.x); x[1] = __uint_as_float(v0.z); x[2] = __uint_as_float(v1.x); x[3] = __uint_as_float(v1.z);
     } else if (a.mode == 3) {
       const uint2 *buf = a.ll + (size_t(par) * a.rep + rep) * 1024;
@@ -237,6 +258,7 @@ int main(int argc, char **argv) {
   CK(cudaMemset(bg, 1, bg_per * G));
   const size_t smem = 4 * 16384;
   CK(cudaFuncSetAttribute(xchg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int G_run = G;
   auto run = [&](int mode, int rep, int sleep_ns, int pollwarps, int work, bool with_bg) {
     CK(cudaMemset(a.ll, 0, sizeof(uint2) * 2 * MAXREP * 1024));
     CK(cudaMemset(a.flags, 0, 4 * 2 * MAXREP * 256));
@@ -248,37 +270,38 @@ int main(int argc, char **argv) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    CK(cudaLaunchCooperativeKernel((void *)xchg_kernel, dim3(G), dim3(NT + 32), args, smem, 0));
+    CK(cudaLaunchCooperativeKernel((void *)xchg_kernel, dim3(G_run), dim3(NT + 32), args, smem, 0));
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    std::vector<long long> cyc(G);
-    CK(cudaMemcpy(cyc.data(), a.cycles, 8 * G, cudaMemcpyDeviceToHost));
+    std::vector<long long> cyc(G_run);
+    CK(cudaMemcpy(cyc.data(), a.cycles, 8 * G_run, cudaMemcpyDeviceToHost));
     long long mx = *std::max_element(cyc.begin(), cyc.end());
     printf("mode %d rep %3d sleep %3d pollwarps %d work %5d bg %d : %7.0f cycles/round  %6.3f us/round\n", mode, rep, sleep_ns,
            pollwarps, work, int(with_bg), double(mx) / a.rounds, ms * 1e3 / a.rounds);
     fflush(stdout);
   };
-  for (int bgf = 0; bgf < 2; ++bgf) {
-    for (int rep : {1, 8, 37, 148}) {
-      for (int sl : {0, 20, 40, 100}) run(0, rep, sl, 0, 0, bgf);
+  auto run2 = [&](int mode, int rep, int pw, int work, int skew, bool with_bg, int relaxed, int grid) {
+    a.skew = skew; a.relaxed = relaxed;
+    CK(cudaMemcpyToSymbol(g_relaxed, &relaxed, sizeof(int)));
+    G_run = grid;
+    run(mode, rep, 0, pw, work, with_bg);
+  };
+  (void)run2;
+  printf("== grid-size scaling (mode 0 rep 8 / mode 3 pw8 rep1), no bg\n");
+  for (int grid : {2, 8, 16, 32, 74, 148}) { printf("grid %d: ", grid); run2(0, 8, 0, 0, 0, false, 0, grid); printf("grid %d: ", grid); run2(3, 1, 8, 0, 0, false, 0, grid); }
+  printf("== relaxed.gpu instead of volatile\n");
+  for (int rl : {0, 1}) { printf("relaxed %d: ", rl); run2(0, 8, 0, 0, 0, false, rl, G); printf("relaxed %d: ", rl); run2(3, 1, 8, 0, 0, false, rl, G); printf("relaxed %d: ", rl); run2(3, 8, 8, 0, 0, false, rl, G); }
+  printf("== skewed arrivals: all-poll (0), smem-poll (3), sentinel (4); work 1000, skew S\n");
+  for (int skew : {0, 500, 2000})
+    for (int bgf : {0, 1}) {
+      printf("skew %d: ", skew); run2(0, 8, 0, 1000, skew, bgf, 0, G);
+      printf("skew %d: ", skew); run2(0, 1, 0, 1000, skew, bgf, 0, G);
+      printf("skew %d: ", skew); run2(3, 1, 8, 1000, skew, bgf, 0, G);
+      printf("skew %d: ", skew); run2(4, 8, 0, 1000, skew, bgf, 0, G);
+      printf("skew %d: ", skew); run2(4, 1, 0, 1000, skew, bgf, 0, G);
+      printf("skew %d: ", skew); run2(2, 8, 0, 1000, skew, bgf, 0, G);
     }
-    for (int rep : {1, 8, 37}) {
-      run(1, rep, 0, 0, 0, bgf);
-      run(1, rep, 40, 0, 0, bgf);
-      run(2, rep, 0, 0, 0, bgf);
-      run(2, rep, 40, 0, 0, bgf);
-    }
-    for (int rep : {1, 8, 37, 148})
-      for (int pw : {1, 2, 4, 8}) run(3, rep, 0, pw, 0, bgf);
-  }
-  // with skewed work between exchanges (does the poll traffic slow the producers down?)
-  for (int work : {500, 2000}) {
-    run(0, 8, 0, 0, work, true);
-    run(0, 8, 40, 0, work, true);
-    run(3, 8, 0, 2, work, true);
-    run(1, 8, 0, 0, work, true);
-  }
   return 0;
 }

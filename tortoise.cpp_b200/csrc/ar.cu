@@ -10,6 +10,7 @@
 #include "wsgemv.cuh"
 #include "ar_mega.cuh"
 #include "ar_mega2.cuh"
+#include "ar_mega3.cuh"
 
 namespace tts {
 
@@ -283,6 +284,18 @@ static void launch_mega2_bt(tts_ctx *c, Mega2Args &a) {
   c->launches += 1;
 }
 
+// Third generation (ar_mega3.cuh): same protocol, GEMV phases on the tensor cores (f16 weights only).
+template <int BT>
+static void launch_mega3_bt(tts_ctx *c, Mega2Args &a) {
+  auto k = ar_decode_mega3_kernel<BT>;
+  static bool attr = false;
+  const size_t smem = mega3_smem_bytes<BT>();
+  if (!attr) { TTS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  void *args[] = {&a};
+  TTS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k, dim3(c->num_sms), dim3(M2_THREADS), args, smem, c->stream));
+  c->launches += 1;
+}
+
 template <typename WT>
 static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
   ArModel &m = c->ar;
@@ -302,6 +315,17 @@ static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
   a.epoch = ++m.mega_epoch;
   a.dbg = m.mega_dbg;
   a.dbg_mode = m.mega_dbg_mode;
+  {
+    static int nrep = -1;
+    if (nrep < 0) { const char *e = getenv("TTS_MEGA_REP"); nrep = e ? std::max(1, std::min(int(M2_REP), atoi(e))) : 2;  // measured on one box: 8 -> 726, 4 -> 680, 2 -> 665, 1 -> 692 us / step }
+    a.nrep = nrep;
+  }
+  if (sizeof(WT) == 2 && !c->use_mega_v2) {
+    if (B == 1) launch_mega3_bt<1>(c, a);
+    else if (B == 2) launch_mega3_bt<2>(c, a);
+    else launch_mega3_bt<4>(c, a);
+    return;
+  }
   if (B == 1) launch_mega2_bt<WT, 1>(c, a);
   else if (B == 2) launch_mega2_bt<WT, 2>(c, a);
   else launch_mega2_bt<WT, 4>(c, a);

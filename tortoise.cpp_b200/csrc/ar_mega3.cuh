@@ -1,150 +1,93 @@
-// ar_mega2.cuh -- AR decode step as one persistent kernel, second generation: the device-wide
-// barriers of ar_mega.cuh are gone.
+// ar_mega3.cuh -- AR decode step as one persistent kernel, third generation (f16 weights):
+// the GEMV of every phase runs on the tensor cores.
 //
-// Same math as ar_mega.cuh / wsgemv.cuh (reference graph autoregressive_graph(fake_inputs=false),
-// main.cpp:2668-3029).  What changed, and why (measured with the in-kernel clock trace,
-// profiles/r01b_mega_trace.md): in the first generation a phase boundary cost 3000-4500 cycles
-// (bar.sync -> MEMBAR.GPU + RED -> one thread polling the counter -> bar.sync -> the L2 round trip
-// that finally fetches the activations) and the LayerNorm prologue another 3000 (two more dependent
-// L2 round trips).  Here
-//   * activations cross CTAs as (value, tag) pairs written with ONE 8-byte store per element
-//     (the low-latency protocol of collective libraries): no fence, no counter, no separate
-//     flag round trip -- a consumer polls the data itself (16-byte volatile loads = two pairs)
-//     and a pair is valid once its tag equals the tag of (launch, layer, phase).  Tags are
-//     unique per launch, so the buffers are never cleared;
-//   * a phase therefore costs store -> L2 -> load, and everything constant a phase needs
-//     (LayerNorm weights, bias) is requested BEFORE the poll;
-//   * attention is split over (candidate, head, key range) items; the K/V tile of a CTA's item
-//     is prefetched into shared memory with cp.async while the QKV phase runs; each item emits
-//     an unnormalised partial (acc[64], max, sum) and the c_proj prologue merges the partials
-//     (exact log-sum-exp merge), so the merge costs no extra exchange;
-//   * per-stage dot products are kept per lane and reduced with shuffles once per phase chunk
-//     (independent chains) instead of once per stage;
-//   * every vector that ALL CTAs read (h, h2, m, attention partials) is written to nrep replicas
-//     (<= M2_REP, default 2) and CTA c polls replica c % nrep: 148 CTAs spinning on the same 64 L2
-//     lines queue on the slices that own them; more replicas multiply the producers' stores
-//     (same-box A/B of the whole step: 8 -> 726 us, 4 -> 680, 2 -> 665, 1 -> 692);
-//   * the step is ONE loop over 121 GEMV phases with a single copy of the GEMV body: the
-//     straight-line version (5 inlined copies, 160 KB of SASS) re-fetched its code from L2 in
-//     every phase;
-//   * the MLP hidden vector (f16-exact after the reference's fp16 GELU table) crosses as
-//     {half2, tag}: half the bytes of the largest per-phase poll;
-//   * up to 4 candidates ride on one weight stream (register-resident activations).
-// Weight streaming is unchanged: a dedicated producer warp walks the whole step's weight slices
-// of this CTA, in consumption order, through a ring of 16 KB stages with 1-D TMA bulk copies.
+// Same math and the same cross-CTA protocol as ar_mega2.cuh (reference graph
+// autoregressive_graph(fake_inputs=false), main.cpp:2668-3029).  What changed, and why
+// (per-CTA globaltimer stamps, profiles/r01_decode_step.md): with the exchange at its floor
+// (~1.5 us per all-to-all of a 1024-vector through L2, tools/xchg_bench.cu) the CUDA-core GEMV
+// was the largest remaining term of the critical path -- 0.8 us fixed + 0.3 us per 16 KB stage
+// although every stage of a phase is resident in shared memory when the phase starts: 64
+// HADD2.F32/FFMA per thread and stage in two dependent chains, a try_wait/arrive per stage, a
+// 5-level shuffle tree per row.  Here
+//   * the producer warp lands every weight row with its own bulk copy at a pitch of K*2 + 16
+//     bytes, so ldmatrix reads 16 x 16 tiles of the row-major [N][K] matrix without bank conflicts;
+//   * the activations are split once per phase into two f16 planes (x = hi + lo, |error| <=
+//     2^-22 |x|) and sit in shared memory as the B operand: columns 0..3 = hi of up to 4
+//     candidates, 4..7 = lo, so ONE mma.sync.m16n8k16 (f32 accumulate; f16 x f16 products are
+//     exact) covers both planes of every candidate.  The MLP hidden vector is f16-exact after
+//     the reference's fp16 GELU table and needs no lo plane;
+//   * each warp owns K/8 of the reduction for ALL rows of the phase (8 or 32 k-steps), waits once
+//     for the phase's stages, and the eight partial tiles are summed through shared memory in a
+//     fixed order (deterministic).
+// Instruction count per phase drops ~10x; 1, 2 or 4 candidates cost the same.
 #pragma once
-#include "ar_mega.cuh"
+#include "ar_mega2.cuh"
 
 namespace tts {
 
-constexpr int M2_CONSUMERS = 256;
-constexpr int M2_THREADS = M2_CONSUMERS + 128;  // + one warpgroup: warp 8 = weight-stream producer, warps 9-11 exit at once
-constexpr int M2_CONSUMER_REGS = 232, M2_PRODUCER_REGS = 24;  // setmaxnreg budgets (the launch allocates 168 x 384)
-constexpr int M2_SMAX = 8;       // max key splits per (candidate, head)
-constexpr int M2_REC = 68;       // pairs per attention partial record: 64 acc, max, sum, 2 pad
-constexpr int M2_KV_TILE = 128;  // keys per attention item
-constexpr int M2_KV_LD = 72;     // halves per K/V row in shared memory (144 B: conflict-free 16-byte reads)
-constexpr int M2_REP = 8;        // replicas of the all-to-all exchange vectors
-
-struct Mega2Args {
-  const MegaLayer *layers;  // [30], device
-  const float *lnf_w, *lnf_b, *lm0_w, *lm0_b, *lm_b;
-  const void *lm_w;
-  const float *mel_emb, *mel_pos;
-  const int *tokens;
-  // (value, tag) exchange buffers; h / h2 / m / att hold M2_REP replicas ([rep][...]); m is
-  // {half2, tag} (kFF / 2 pairs per candidate)
-  uint2 *ll_h, *ll_h2, *ll_qkv, *ll_m, *ll_att;
-  float *logits;
-  __half *kc, *vc;  // [30][Bmax][16][P][64]
-  int B, Bmax, P, n_past, pos_id;
-  unsigned int epoch;  // unique per launch (1 .. 2^24-1)
-  long long *dbg;      // optional clock trace (TTS_MEGA_TRACE=1: CTA 0, cycle stamps; =2: every CTA, 4 globaltimer stamps per phase)
-  int dbg_mode;
-  int nrep;  // replicas of the all-to-all vectors in use (1..M2_REP; TTS_MEGA_REP)
-};
+constexpr int M3_STAGES = 8;                       // ring depth
+constexpr int M3_ROWS_K1 = 8, M3_ROWS_K4 = 2;      // weight rows per stage at K = 1024 / 4096 (16 KB of weights)
+constexpr int M3_PITCH_K1 = kDim * 2 + 16;         // bytes between rows in shared memory (conflict-free ldmatrix)
+constexpr int M3_PITCH_K4 = kFF * 2 + 16;
+constexpr int M3_STAGE_SMEM = M3_ROWS_K1 * M3_PITCH_K1;  // 16512 (>= 2 x 8208)
+constexpr int M3_GROUP = 4;                        // stages consumed together (<= 32 rows at K = 1024, 8 at K = 4096)
+constexpr int M3_XP_K1 = kDim + 8, M3_XP_K4 = kFF + 8;   // halves between rows of the activation planes
 
 template <int BT>
-struct M2Cfg {
-  static constexpr int kStages = BT == 4 ? 6 : 8;  // ring depth (16 KB stages)
-  static constexpr int kChunk = BT == 1 ? 4 : (BT == 2 ? 2 : 1);  // stages loaded and reduced together (register budget)
-};
+__host__ __device__ inline size_t mega3_smem_bytes() {
+  return size_t(M3_STAGES) * M3_STAGE_SMEM + 256 /*mbarriers*/ + size_t(8) * 32 * BT * sizeof(float) /*partial tiles*/ +
+         64 * sizeof(double) /*LN sums*/ + size_t(BT) * M3_XP_K4 * sizeof(__half) /*activation planes*/ +
+         size_t(BT) * kDim * sizeof(float) /*residual*/ + size_t(2) * M2_KV_TILE * M2_KV_LD * sizeof(__half) /*K, V tile*/ +
+         (128 + 64 + 8 * 64 + 32) * sizeof(float);
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// x = hi + lo in f16 (lo = f16(x - hi))
+__device__ __forceinline__ void split16(float x0, float x1, __half2 &hi, __half2 &lo) {
+  hi = __floats2half2_rn(x0, x1);
+  const float2 h = __half22float2(hi);
+  lo = __floats2half2_rn(x0 - h.x, x1 - h.y);
+}
 
 template <int BT>
-__host__ __device__ inline size_t mega2_smem_bytes() {
-  return size_t(M2Cfg<BT>::kStages) * GV_STAGE_BYTES + 256 /*mbarriers*/ +
-         size_t(GV_MAX_ROWS_PER_CTA) * 8 * BT * sizeof(float) /*partials*/ + 64 * sizeof(double) /*LN sums*/ +
-         size_t(BT) * kFF * sizeof(float) /*phase input*/ + size_t(BT) * kDim * sizeof(float) /*residual*/ +
-         size_t(2) * M2_KV_TILE * M2_KV_LD * sizeof(__half) /*K, V tile*/ + (128 + 64 + 8 * 64 + 32) * sizeof(float);
-}
-
-__device__ __forceinline__ uint4 ld_ll(const uint2 *p) {  // two (value, tag) pairs
-  uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p)
-               : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_ll_u32(uint2 *p, uint32_t bits, uint32_t tag) {
-  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(bits), "r"(tag) : "memory");
-}
-__device__ __forceinline__ void st_ll(uint2 *p, float val, uint32_t tag) { st_ll_u32(p, __float_as_uint(val), tag); }
-__device__ __forceinline__ void cp_async_cg16(void *dst_smem, const void *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// Between two polls of a tag that has not arrived.  Measured (tools/xchg_bench.cu): __nanosleep(40)
-// costs ~1800 cycles per call on B200 whatever its argument, i.e. it quantises every exchange to
-// multiples of ~1 us; a plain re-poll (one L2 round trip, ~300 cycles) is the cheapest wait.
-__device__ __forceinline__ void poll_backoff() {}
-__device__ __forceinline__ long long global_ns() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-template <typename WT, int BT>
-static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(Mega2Args a) {
-  constexpr int E = WTraits<WT>::kElemsPer16B;
-  constexpr int KS = 32 * 4 * E;  // K elements of one warp's 2 KB slice
-  constexpr int STAGES = M2Cfg<BT>::kStages;
-  constexpr int CH = M2Cfg<BT>::kChunk;
+static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(Mega2Args a) {
+  static_assert(BT == 1 || BT == 2 || BT == 4, "hi and lo planes of every candidate share one n = 8 MMA tile");
+  constexpr int STAGES = M3_STAGES;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *ring = smem;
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * GV_STAGE_BYTES);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * M3_STAGE_SMEM);
   uint64_t *empty = full + STAGES;
-  float *partial = reinterpret_cast<float *>(smem + STAGES * GV_STAGE_BYTES + 256);
-  double *red = reinterpret_cast<double *>(partial + GV_MAX_ROWS_PER_CTA * 8 * BT);
-  float *xin = reinterpret_cast<float *>(red + 64);  // [BT][kFF] input vector of the running phase
-  float *hres = xin + BT * kFF;                      // [BT][kDim] residual stream
+  float *partial = reinterpret_cast<float *>(smem + STAGES * M3_STAGE_SMEM + 256);  // [8 warps][32 rows][BT]
+  double *red = reinterpret_cast<double *>(partial + 8 * 32 * BT);
+  // activation planes (B operand): K = 1024 phases: rows 0..BT-1 = hi, BT..2BT-1 = lo, pitch M3_XP_K1;
+  // K = 4096 phase: rows 0..BT-1 = hi only, pitch M3_XP_K4
+  __half *xs = reinterpret_cast<__half *>(red + 64);
+  float *hres = reinterpret_cast<float *>(xs + BT * M3_XP_K4);  // [BT][kDim] residual stream
   __half *kt = reinterpret_cast<__half *>(hres + BT * kDim);  // [128][72] K tile
   __half *vt = kt + M2_KV_TILE * M2_KV_LD;                    // [128][72] V tile
   float *sc = reinterpret_cast<float *>(vt + M2_KV_TILE * M2_KV_LD);  // [128] scores
   float *qs = sc + 128;                                               // [64] query
   float *pp = qs + 64;                                                // [8][64] partial outputs
   float *redf = pp + 8 * 64;                                          // [32] block reductions
-
-  // the layer table (pointers) and this CTA's row slices live in shared memory: a pointer fetched
-  // from global memory in front of every dependent load, or an integer division per phase, stalls
-  // the in-order issue of a phase that is only a few thousand cycles long
+  // the layer table (pointers) lives in shared memory: a pointer fetched from global memory in
+  // front of every dependent load stalls the in-order issue for an L2 round trip
   __shared__ MegaLayer s_layers[kLayers];
-  __shared__ int s_slice[4][2];  // {row0, rows} for N = 3072, 1024, 4096, 8194
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
   const int B = a.B;
   for (int i = tid; i < int(kLayers * sizeof(MegaLayer) / 8); i += M2_THREADS)
     reinterpret_cast<unsigned long long *>(s_layers)[i] = reinterpret_cast<const unsigned long long *>(a.layers)[i];
-  if (tid < 4) {
-    // the c_fc slices start and end on even rows (its outputs are exchanged as half2 pairs)
-    const int N = tid == 0 ? 3072 : (tid == 1 ? kDim : (tid == 2 ? kFF : kMelVocab));
-    const int gran = N == kFF ? 2 : 1;
-    const int U = N / gran, base = U / G, rem = U % G;
-    s_slice[tid][1] = gran * (base + (cta < rem ? 1 : 0));
-    s_slice[tid][0] = gran * (cta * base + min(cta, rem));
-  }
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -165,16 +108,16 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
       default: N = kDim; K = kFF; W = l.w_proj2; break;
     }
   };
-  // rows of a matrix owned by this CTA
+  // rows of a matrix owned by this CTA; the c_fc slices start and end on even rows (its outputs
+  // are exchanged as half2 pairs)
   auto slice = [&](int N, int &row0, int &rows) {
-    const int i = N == 3072 ? 0 : (N == kDim ? 1 : (N == kFF ? 2 : 3));
-    row0 = s_slice[i][0];
-    rows = s_slice[i][1];
+    const int gran = N == kFF ? 2 : 1;
+    const int U = N / gran, base = U / G, rem = U % G;
+    rows = gran * (base + (cta < rem ? 1 : 0));
+    row0 = gran * (cta * base + min(cta, rem));
   };
 
   if (warp >= M2_CONSUMERS / 32) {
-    // the producer warpgroup hands its registers to the consumers (9 warps would put three on one
-    // scheduler and cap everybody at 168 registers: the GEMV body spills)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(M2_PRODUCER_REGS));
     // ---------------- weight stream: every slice of the step, in consumption order ------------
     if (warp == M2_CONSUMERS / 32 && lane == 0) {
@@ -184,15 +127,15 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
         const void *W;
         seg_shape(sid, N, K, W);
         slice(N, row0, rows);
-        const size_t row_bytes = size_t(K) * sizeof(WT);
+        const uint32_t row_bytes = uint32_t(K) * 2u;
+        const int rps = K == kDim ? M3_ROWS_K1 : M3_ROWS_K4, pitch = K == kDim ? M3_PITCH_K1 : M3_PITCH_K4;
         const unsigned char *src = reinterpret_cast<const unsigned char *>(W) + size_t(row0) * row_bytes;
-        const size_t total = size_t(rows) * row_bytes;
-        for (size_t off = 0; off < total; off += GV_STAGE_BYTES, ++it) {
-          const int slot = int(it % STAGES);
+        for (int r0 = 0; r0 < rows; r0 += rps, ++it) {
+          const int slot = int(it % STAGES), nr = min(rps, rows - r0);
           mbar_wait(&empty[slot], uint32_t((it / STAGES) & 1) ^ 1u);
-          const uint32_t bytes = uint32_t(min(size_t(GV_STAGE_BYTES), total - off));
-          mbar_arrive_expect_tx(&full[slot], bytes);
-          bulk_g2s(ring + size_t(slot) * GV_STAGE_BYTES, src + off, bytes, &full[slot]);
+          mbar_arrive_expect_tx(&full[slot], uint32_t(nr) * row_bytes);
+          for (int r = 0; r < nr; ++r)
+            bulk_g2s(ring + size_t(slot) * M3_STAGE_SMEM + r * pitch, src + size_t(r0 + r) * row_bytes, row_bytes, &full[slot]);
         }
       }
     }
@@ -475,14 +418,18 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
           }
       }
       const float inv = 1.0f / L;
-      *reinterpret_cast<float4 *>(xin + b * kFF + head * kHeadDim + d0) =
-          make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+      __half2 h0, l0, h1, l1;
+      split16(o[0] * inv, o[1] * inv, h0, l0);
+      split16(o[2] * inv, o[3] * inv, h1, l1);
+      const int k = head * kHeadDim + d0;
+      *reinterpret_cast<uint2 *>(xs + b * M3_XP_K1 + k) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+      *reinterpret_cast<uint2 *>(xs + (BT + b) * M3_XP_K1 + k) = make_uint2(*reinterpret_cast<uint32_t *>(&l0), *reinterpret_cast<uint32_t *>(&l1));
     }
   };
 
   // =========================== the step: 30 x (QKV | c_proj | c_fc | mlp c_proj) + lm_head ==========
   // One loop, one copy of the GEMV body.  Phase p of layer li: prologue (what xin holds), then
-  // xin x this CTA's rows of the phase's matrix, then the epilogue that feeds the next phase.
+  // the activation planes x this CTA's rows of the phase's matrix, then the epilogue that feeds the next phase.
   float lw[4], lb[4];
   constexpr int kPhases = kLayers * 4 + 1;
   for (int ph = 0; ph < kPhases; ++ph) {
@@ -520,8 +467,13 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
       }
 #pragma unroll
       for (int b = 0; b < BT; ++b) {
-        *reinterpret_cast<float2 *>(xin + b * kFF + 2 * tid) = make_float2(hv[b][0], hv[b][1]);
-        *reinterpret_cast<float2 *>(xin + b * kFF + 512 + 2 * tid) = make_float2(hv[b][2], hv[b][3]);
+        __half2 h0, l0, h1, l1;
+        split16(hv[b][0], hv[b][1], h0, l0);
+        split16(hv[b][2], hv[b][3], h1, l1);
+        *reinterpret_cast<__half2 *>(xs + b * M3_XP_K1 + 2 * tid) = h0;
+        *reinterpret_cast<__half2 *>(xs + b * M3_XP_K1 + 512 + 2 * tid) = h1;
+        *reinterpret_cast<__half2 *>(xs + (BT + b) * M3_XP_K1 + 2 * tid) = l0;
+        *reinterpret_cast<__half2 *>(xs + (BT + b) * M3_XP_K1 + 512 + 2 * tid) = l1;
       }
     } else if (p == 1) {
       trace(11);
@@ -546,9 +498,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
             poll_backoff();
             v[u] = ld_ll(src + 2 * (tid + u * M2_CONSUMERS));
           }
-          const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&v[u].x));
-          const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&v[u].z));
-          *reinterpret_cast<float4 *>(xin + b * kFF + 4 * (tid + u * M2_CONSUMERS)) = make_float4(f0.x, f0.y, f1.x, f1.y);
+          *reinterpret_cast<uint2 *>(xs + b * M3_XP_K4 + 4 * (tid + u * M2_CONSUMERS)) = make_uint2(v[u].x, v[u].z);
         }
       }
     }
@@ -556,147 +506,152 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
     trace(20 + p);
     stamp(ph, 1);
 
-    // ---------------- GEMV: xin (shared) x this CTA's weight rows (ring) ----------------
+    // ---------------- GEMV on the tensor cores: D[rows x 8] = W[rows x K] . X[K x 8] ----------------
     // kind: 0 = QKV (f16 round trip, KV append), 1 = residual, 2 = GELU16, 3 = logits
     const int N = tail ? kMelVocab : (p == 0 ? 3072 : (p == 2 ? kFF : kDim));
-    const int K = p == 3 ? kFF : kDim;
+    const bool k4 = p == 3;  // K = 4096
     const int kind = tail ? 3 : (p == 0 ? 0 : (p == 2 ? 2 : 1));
     const float *bias = tail ? a.lm_b : (p == 0 ? l.b_qkv : (p == 1 ? l.b_proj : (p == 2 ? l.b_fc : l.b_proj2)));
     const uint32_t out_tag = tag_of(li, p == 0 ? 1 : (p == 1 ? 3 : (p == 2 ? 4 : 5)));
     {
-      // (all shapes are powers of two: no runtime division)
-      constexpr int WPR1 = kDim / KS, WPR4 = kFF / KS;  // warps per weight row
-      const bool k4 = p == 3;
-      const int wpr = k4 ? WPR4 : WPR1, rps = k4 ? GV_WARPS / WPR4 : GV_WARPS / WPR1;
-      const int rlog = 31 - __clz(rps);
+      const int rps = k4 ? M3_ROWS_K4 : M3_ROWS_K1, pitch = k4 ? M3_PITCH_K4 : M3_PITCH_K1, xp = k4 ? M3_XP_K4 : M3_XP_K1;
+      const int ksteps = k4 ? 32 : 8;                    // 16-wide k steps of this warp's K / 8 slice
+      const int kbase = warp * ksteps * 16;
       int row0, rows_cta;
       slice(N, row0, rows_cta);
-      const int n_stages = (rows_cta + rps - 1) >> rlog;
-      const int ks = warp & (wpr - 1), rsub = warp >> (31 - __clz(wpr));
-      float ep_bias = 0.f;
-      if (tid < rows_cta * BT) ep_bias = bias[row0 + tid / BT];
-      float xr[BT][4][E];
-#pragma unroll
-      for (int b = 0; b < BT; ++b)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = ks * KS + j * (32 * E) + lane * E;
-#pragma unroll
-          for (int e4 = 0; e4 < E; e4 += 4) {
-            const float4 v = *reinterpret_cast<const float4 *>(xin + b * kFF + k + e4);
-            xr[b][j][e4 + 0] = v.x; xr[b][j][e4 + 1] = v.y; xr[b][j][e4 + 2] = v.z; xr[b][j][e4 + 3] = v.w;
-          }
+      const int n_stages = (rows_cta + rps - 1) / rps;
+      // B fragment source: column n = lane / 4 of the n = 8 tile -> plane row (hi: n < 4, lo: n >= 4)
+      const int ncol = lane >> 2;
+      const int cand = ncol & 3;
+      const bool col_on = cand < BT && !(k4 && ncol >= 4);
+      const int xrow = (ncol < 4 ? 0 : BT) + cand;
+      const uint32_t xaddr = smem_u32(xs) + uint32_t((col_on ? xrow : 0) * xp + kbase + (lane & 3) * 2) * 2u;
+      // A fragment source: ldmatrix lane -> (row within the 16-row tile, k half)
+      const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kofs = (lane >> 4) * 8;
+      for (int s0 = 0; s0 < n_stages; s0 += M3_GROUP) {
+        const int gs = min(M3_GROUP, n_stages - s0);          // stages of this group
+        const int grow0 = s0 * rps, grows = min(gs * rps, rows_cta - grow0);  // rows of this group
+        float ep_bias = 0.f;
+        if (tid < grows * BT) ep_bias = bias[row0 + grow0 + tid / BT];
+        for (int j = 0; j < gs; ++j) {
+          const int slot = int((c_it + j) % STAGES);
+          mbar_wait(&full[slot], uint32_t(((c_it + j) / STAGES) & 1));
         }
-      trace(40);
-      // CH stages at a time: every wait, then every shared-memory load, then the arithmetic (the
-      // stages of a phase are resident when it starts; serialising wait -> load -> FMA chain ->
-      // arrive per stage was ~600 cycles per stage)
-      for (int s0 = 0; s0 < n_stages; s0 += CH) {
-        const int gs = min(CH, n_stages - s0);
-#pragma unroll
-        for (int j = 0; j < CH; ++j)
-          if (j < gs) mbar_wait(&full[int((c_it + j) % STAGES)], uint32_t(((c_it + j) / STAGES) & 1));
         trace(50);
-        // straight-line, branch-free: rows past the slice read zeros, so the scheduler can interleave
-        // the 4 CH BT independent FMA chains (a phase is latency-bound: ~3 cycles per instruction
-        // with two warps per scheduler and dependent chains)
-        uint4 wv[CH][4];
-        bool valid[CH];
+        const int mtiles = (grows + 15) >> 4;  // 1 or 2
+        uint32_t aaddr[2];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          const int r = (s0 + j) * rps + rsub;
-          valid[j] = j < gs && r < rows_cta;
-          const unsigned char *wp = ring + size_t((c_it + j) % STAGES) * GV_STAGE_BYTES + warp * 2048 + lane * 16;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) wv[j][q] = valid[j] ? *reinterpret_cast<const uint4 *>(wp + q * 512) : make_uint4(0, 0, 0, 0);
+        for (int mt = 0; mt < 2; ++mt) {
+          int gr = mt * 16 + a_row;
+          if (gr >= grows) gr = 0;  // rows past the slice: any resident row (results unused)
+          const int slot = int((c_it + gr / rps) % STAGES);
+          aaddr[mt] = smem_u32(ring) + uint32_t(slot * M3_STAGE_SMEM + (gr % rps) * pitch + (kbase + a_kofs) * 2);
         }
-        float acc[CH][BT];
+        // Batches of four independent (ldmatrix, mma) pairs: every load of a batch is issued before
+        // its first mma, and the four mma of a batch feed four different accumulators, so the
+        // chain per batch is one shared-memory latency + one mma latency.
+        float acc[4][4];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          float aq[4][BT];
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float wf[E];
-            if constexpr (sizeof(WT) == 4) {
-              wf[0] = __uint_as_float(wv[j][q].x);
-              wf[1] = __uint_as_float(wv[j][q].y);
-              wf[2] = __uint_as_float(wv[j][q].z);
-              wf[3] = __uint_as_float(wv[j][q].w);
-            } else {
-              const __half2 *h2 = reinterpret_cast<const __half2 *>(&wv[j][q]);
+          for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+        auto ldb = [&](int ks, uint32_t &b0, uint32_t &b1) {
+          b0 = 0; b1 = 0;
+          if (col_on) {
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b0) : "r"(xaddr + ks * 32));
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b1) : "r"(xaddr + ks * 32 + 16));
+          }
+        };
+        if (mtiles == 2) {
+          // acc[0], acc[1]: row tile 0 (even / odd k step); acc[2], acc[3]: row tile 1
+          for (int ks = 0; ks < ksteps; ks += 2) {
+            uint32_t b[2][2], fa[4][4];
+            ldb(ks, b[0][0], b[0][1]);
+            ldb(ks + 1, b[1][0], b[1][1]);
+            ldmatrix_x4(aaddr[0] + ks * 32, fa[0][0], fa[0][1], fa[0][2], fa[0][3]);
+            ldmatrix_x4(aaddr[0] + ks * 32 + 32, fa[1][0], fa[1][1], fa[1][2], fa[1][3]);
+            ldmatrix_x4(aaddr[1] + ks * 32, fa[2][0], fa[2][1], fa[2][2], fa[2][3]);
+            ldmatrix_x4(aaddr[1] + ks * 32 + 32, fa[3][0], fa[3][1], fa[3][2], fa[3][3]);
+            mma_16816(acc[0], fa[0][0], fa[0][1], fa[0][2], fa[0][3], b[0][0], b[0][1]);
+            mma_16816(acc[1], fa[1][0], fa[1][1], fa[1][2], fa[1][3], b[1][0], b[1][1]);
+            mma_16816(acc[2], fa[2][0], fa[2][1], fa[2][2], fa[2][3], b[0][0], b[0][1]);
+            mma_16816(acc[3], fa[3][0], fa[3][1], fa[3][2], fa[3][3], b[1][0], b[1][1]);
+          }
 #pragma unroll
-              for (int qd = 0; qd < 4; ++qd) {
-                const float2 f = __half22float2(h2[qd]);
-                wf[2 * qd] = f.x;
-                wf[2 * qd + 1] = f.y;
+          for (int q = 0; q < 4; ++q) { acc[0][q] += acc[1][q]; acc[1][q] = acc[2][q] + acc[3][q]; }
+        } else {
+          for (int ks = 0; ks < ksteps; ks += 4) {
+            uint32_t b[4][2], fa[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ldb(ks + i, b[i][0], b[i][1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ldmatrix_x4(aaddr[0] + (ks + i) * 32, fa[i][0], fa[i][1], fa[i][2], fa[i][3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mma_16816(acc[i], fa[i][0], fa[i][1], fa[i][2], fa[i][3], b[i][0], b[i][1]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[0][q] = (acc[0][q] + acc[1][q]) + (acc[2][q] + acc[3][q]);
+        }
+        trace(45);
+        __syncwarp();
+        if (lane == 0)
+          for (int j = 0; j < gs; ++j) mbar_arrive(&empty[int((c_it + j) % STAGES)]);
+        c_it += gs;
+        // hi + lo planes: columns c and c + 4 sit two lanes apart
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt < mtiles) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[mt][q] += __shfl_xor_sync(0xffffffffu, acc[mt][q], 2);
+            if ((lane & 3) < 2) {
+              const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int cc = c + (q & 1), rr = r + (q >> 1) * 8;
+                if (cc < BT) partial[(warp * 32 + rr) * BT + cc] = acc[mt][q];
               }
             }
+          }
+        }
+        trace(46);
+        bar_consumers();
+        if (s0 == 0) { trace(30 + p); stamp(ph, 2); }
+        // ---------------- epilogue: one output element per thread ----------------
+        const bool act = tid < grows * BT && (tid % BT) < B;
+        const int r = tid / BT, b = tid % BT, n = row0 + grow0 + r;
+        float v = 0.f;
+        if (act) {
 #pragma unroll
-            for (int b = 0; b < BT; ++b) {
-              float t = wf[0] * xr[b][q][0];
-#pragma unroll
-              for (int e = 1; e < E; ++e) t = fmaf(wf[e], xr[b][q][e], t);
-              aq[q][b] = t;
+          for (int w = 0; w < GV_WARPS; ++w) v += partial[(w * 32 + r) * BT + b];
+          v += ep_bias;
+          if (kind == 2) v = gelu16(v);
+        }
+        // (c_fc: rows n, n+1 of one candidate sit BT lanes apart; its slices start on even rows)
+        const float v_next = __shfl_down_sync(0xffffffffu, v, BT);
+        if (act) {
+          if (kind == 0) {
+            const __half hv16 = __float2half_rn(v);
+            st_ll(a.ll_qkv + size_t(b) * 3072 + n, __half2float(hv16), out_tag);
+            const int which = n >> 10, c = n & 1023;
+            if (which != 0) {
+              __half *cache = (which == 1 ? a.kc : a.vc) + size_t(li) * layer_kv;
+              cache[(size_t(b) * kHeads + (c >> 6)) * size_t(a.P) * kHeadDim + size_t(a.n_past) * kHeadDim + (c & 63)] = hv16;
             }
-          }
-#pragma unroll
-          for (int b = 0; b < BT; ++b) acc[j][b] = (aq[0][b] + aq[2][b]) + (aq[1][b] + aq[3][b]);
-        }
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (j < gs) mbar_arrive(&empty[int((c_it + j) % STAGES)]);
-        }
-        c_it += gs;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-#pragma unroll
-          for (int b = 0; b < BT; ++b) {
-            const float v = warp_sum(acc[j][b]);
-            if (lane == 0 && valid[j]) partial[(((s0 + j) * rps + rsub) * 8 + ks) * BT + b] = v;
+          } else if (kind == 1) {
+            const float o = hres[b * kDim + n] + v;
+            uint2 *dst = (p == 1 ? a.ll_h2 : a.ll_h) + size_t(b) * kDim + n;
+            for (int rr = 0; rr < nrep; ++rr) st_ll(dst + rr * h_rep, o, out_tag);
+          } else if (kind == 2) {
+            if ((r & 1) == 0) {
+              const __half2 h2 = __floats2half2_rn(v, v_next);  // exact: gelu16 outputs are f16 values
+              uint2 *dst = a.ll_m + size_t(b) * (kFF / 2) + (n >> 1);
+              for (int rr = 0; rr < nrep; ++rr) st_ll_u32(dst + rr * m_rep, *reinterpret_cast<const uint32_t *>(&h2), out_tag);
+            }
+          } else {
+            a.logits[size_t(b) * N + n] = v;
           }
         }
-      }
-      trace(45);
-      bar_consumers();
-      trace(30 + p);
-      stamp(ph, 2);
-      // ---------------- epilogue: one output element per thread ----------------
-      const bool act = tid < rows_cta * BT && (tid % BT) < B;
-      const int r = tid / BT, b = tid % BT, n = row0 + r;
-      float v = 0.f;
-      if (act) {
-        for (int w = 0; w < wpr; ++w) v += partial[(r * 8 + w) * BT + b];
-        v += ep_bias;
-        if (kind == 2) v = gelu16(v);
-      }
-      // (c_fc: rows n, n+1 of one candidate sit BT lanes apart; its slices start on even rows)
-      const float v_next = __shfl_down_sync(0xffffffffu, v, BT);
-      if (act) {
-        if (kind == 0) {
-          const __half hv16 = __float2half_rn(v);
-          st_ll(a.ll_qkv + size_t(b) * 3072 + n, __half2float(hv16), out_tag);
-          const int which = n >> 10, c = n & 1023;
-          if (which != 0) {
-            __half *cache = (which == 1 ? a.kc : a.vc) + size_t(li) * layer_kv;
-            cache[(size_t(b) * kHeads + (c >> 6)) * size_t(a.P) * kHeadDim + size_t(a.n_past) * kHeadDim + (c & 63)] = hv16;
-          }
-        } else if (kind == 1) {
-          const float o = hres[b * kDim + n] + v;
-          uint2 *dst = (p == 1 ? a.ll_h2 : a.ll_h) + size_t(b) * kDim + n;
-#pragma unroll
-          for (int rr = 0; rr < nrep; ++rr) st_ll(dst + rr * h_rep, o, out_tag);
-        } else if (kind == 2) {
-          if ((r & 1) == 0) {
-            const __half2 h2 = __floats2half2_rn(v, v_next);  // exact: gelu16 outputs are f16 values
-            uint2 *dst = a.ll_m + size_t(b) * (kFF / 2) + (n >> 1);
-#pragma unroll
-            for (int rr = 0; rr < nrep; ++rr) st_ll_u32(dst + rr * m_rep, *reinterpret_cast<const uint32_t *>(&h2), out_tag);
-          }
-        } else {
-          a.logits[size_t(b) * N + n] = v;
-        }
+        if (s0 + M3_GROUP < n_stages) bar_consumers();  // the next group overwrites the partial tiles
       }
     }
     stamp(ph, 3);

@@ -91,6 +91,7 @@ struct tts_ctx {
   bool use_graph = true;
   bool use_pdl = true;
   bool use_mega = true;   // persistent single-kernel decode step (TTS_NO_MEGA=1 -> per-op graph path)
+  bool use_mega_v2 = false;  // TTS_MEGA_V2=1: CUDA-core GEMV phases also for f16 weights (default: tensor-core ar_mega3.cuh)
   bool use_mega_v1 = false;  // TTS_MEGA_V1=1: first-generation persistent step (grid barriers), for A/B
   tts::ArModel ar;
   tts::ArState ars;

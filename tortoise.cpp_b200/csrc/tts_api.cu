@@ -72,6 +72,7 @@ int tts_init(const tts_config *cfg, tts_ctx **out) {
   const char *em = getenv("TTS_NO_MEGA");
   c->use_mega = !(em && em[0] == '1');
   { const char *e1 = getenv("TTS_MEGA_V1"); c->use_mega_v1 = e1 && e1[0] == '1'; }
+  { const char *e2 = getenv("TTS_MEGA_V2"); c->use_mega_v2 = e2 && e2[0] == '1'; }
   try {
     TTS_CUDA_TRY(cudaSetDevice(cfg->device));
     TTS_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
