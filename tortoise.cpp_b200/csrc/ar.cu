@@ -317,7 +317,7 @@ static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
   a.dbg_mode = m.mega_dbg_mode;
   {
     static int nrep = -1;
-    if (nrep < 0) { const char *e = getenv("TTS_MEGA_REP"); nrep = e ? std::max(1, std::min(int(M2_REP), atoi(e))) : 2;  // measured on one box: 8 -> 726, 4 -> 680, 2 -> 665, 1 -> 692 us / step }
+    if (nrep < 0) { const char *e = getenv("TTS_MEGA_REP"); nrep = e ? std::max(1, std::min(int(M2_REP), atoi(e))) : 2; }  // same-box A/B: 8 -> 726, 4 -> 680, 2 -> 665, 1 -> 692 us / step
     a.nrep = nrep;
   }
   if (sizeof(WT) == 2 && !c->use_mega_v2) {
