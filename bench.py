@@ -48,6 +48,12 @@ GOLDEN_MODELS = os.path.join(ROOT, "tests", "golden", "models")
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one decode-step launch, from the committed
+# `ncu --set full` capture (profiles/); per launch like `achieved`
+NCU_TRAFFIC_BYTES = 776239616 + 7129344
+NCU_TRAFFIC_SOURCE = "profiles/r01c_mega2_ncu_full_raw.csv (ar_decode_mega2_kernel<__half,1>, same weight stream)"
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -325,10 +331,11 @@ def main():
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
-                     "kernel": "ar_decode_mega_kernel<__half,1>: one launch = one decode step of 1 candidate "
-                               "(30 layers x 4 GEMVs + attention + lm_head); bytes = 386.29 M weights x 2 B + KV + "
-                               "embeddings + logits",
+                     "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE,
+                     "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                     "kernel": "ar_decode_mega3_kernel<1>: one launch = one decode step of 1 candidate "
+                               "(30 layers x 4 GEMV phases + attention + lm_head, persistent, 148 CTAs); bytes = "
+                               "386.29 M weights x 2 B + KV + embeddings + logits",
                      "us_per_launch": step_ms * 1e3, "bytes_per_launch": step_bytes,
                      "per_op_wsgemv_kernel": per_op},
     }
