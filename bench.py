@@ -50,8 +50,8 @@ HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one decode-step launch, from the committed
 # `ncu --set full` capture (profiles/); per launch like `achieved`
-NCU_TRAFFIC_BYTES = 776239616 + 7129344
-NCU_TRAFFIC_SOURCE = "profiles/r01c_mega2_ncu_full_raw.csv (ar_decode_mega2_kernel<__half,1>, same weight stream)"
+NCU_TRAFFIC_BYTES = 776120064 + 5641216
+NCU_TRAFFIC_SOURCE = "profiles/r01d_mega3_ncu_full_raw.csv (ar_decode_mega3_kernel<1>, ~20 cached positions)"
 
 
 def measured_peaks():
