@@ -319,6 +319,15 @@ static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
     static int nrep = -1;
     if (nrep < 0) { const char *e = getenv("TTS_MEGA_REP"); nrep = e ? std::max(1, std::min(int(M2_REP), atoi(e))) : 2; }  // same-box A/B: 8 -> 726, 4 -> 680, 2 -> 665, 1 -> 692 us / step
     a.nrep = nrep;
+    static int defer = -1;
+    if (defer < 0) { const char *e = getenv("TTS_MEGA_NODEFER"); defer = (e && e[0] == '1') ? 0 : 1; }
+    a.defer = defer;
+    static int spin = -1;
+    if (spin < 0) { const char *e = getenv("TTS_MEGA_SPIN"); spin = e ? atoi(e) : 0; }
+    a.poll_spin = spin;
+    static int kps = -1;
+    if (kps < 0) { const char *e = getenv("TTS_MEGA_KPS"); kps = e ? std::max(8, std::min(128, atoi(e))) : 128; }
+    a.keys_per_split = kps;
   }
   if (sizeof(WT) == 2 && !c->use_mega_v2) {
     if (B == 1) launch_mega3_bt<1>(c, a);

@@ -61,6 +61,9 @@ struct Mega2Args {
   unsigned int epoch;  // unique per launch (1 .. 2^24-1)
   long long *dbg;      // optional clock trace (TTS_MEGA_TRACE=1: CTA 0, cycle stamps; =2: every CTA, 4 globaltimer stamps per phase)
   int dbg_mode;
+  int keys_per_split;  // attention: keys per (candidate, head) item before splitting (TTS_MEGA_KPS)
+  int poll_spin;  // cycles between two polls of a missing tag (TTS_MEGA_SPIN)
+  int defer;  // 1: deferred ring-slot release (default)
   int nrep;  // replicas of the all-to-all vectors in use (1..M2_REP; TTS_MEGA_REP)
 };
 
@@ -97,7 +100,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Between two polls of a tag that has not arrived.  Measured (tools/xchg_bench.cu): __nanosleep(40)
 // costs ~1800 cycles per call on B200 whatever its argument, i.e. it quantises every exchange to
 // multiples of ~1 us; a plain re-poll (one L2 round trip, ~300 cycles) is the cheapest wait.
-__device__ __forceinline__ void poll_backoff() {}
+__device__ __forceinline__ void poll_backoff(int spin) {
+  if (spin > 0) {  // a short clock spin thins out the re-polls (fewer requests queued on the hot L2 lines)
+    const long long t0 = clock64();
+    while (clock64() - t0 < spin) {
+    }
+  }
+}
 __device__ __forceinline__ long long global_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -212,6 +221,8 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
   const uint32_t tag_base = a.epoch << 8;
   auto tag_of = [&](int layer, int phase) { return tag_base + uint32_t(layer * 8 + phase); };
   long c_it = 0;  // ring stage counter (same order as the producer)
+  long rel_it = 0;  // first stage of the group whose slots are still held
+  int rel_n = 0;
   const int nb = min(a.Bmax, 4);  // candidates the exchange buffers are sized for
   const int nrep = a.nrep;       // replicas in use (<= M2_REP)
   const int rep = cta % nrep;   // the replica this CTA reads
@@ -221,7 +232,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
   auto poll_unit = [&](const uint2 *p, uint32_t tag) -> float2 {
     uint4 v = ld_ll(p);
     while (v.y != tag || v.w != tag) {
-      poll_backoff();
+      poll_backoff(a.poll_spin);
       v = ld_ll(p);
     }
     return make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
@@ -243,7 +254,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           while (v[b][u].y != tag || v[b][u].w != tag) {
-            poll_backoff();
+            poll_backoff(a.poll_spin);
             v[b][u] = ld_ll(buf + size_t(b) * kDim + u * 512 + 2 * tid);
           }
           hv[b][2 * u] = __uint_as_float(v[b][u].x);
@@ -304,7 +315,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
   int S;
   {
     const int cap = max(1, min(4, G / (kHeads * B)));
-    S = min(cap, (n_keys + 31) / 32);
+    S = min(cap, (n_keys + a.keys_per_split - 1) / a.keys_per_split);
     S = max(S, (n_keys + M2_KV_TILE - 1) / M2_KV_TILE);
     S = max(1, min(S, M2_SMAX));
   }
@@ -458,7 +469,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
 #pragma unroll
             for (int u = 0; u < 3; ++u)
               while (v[i][u].y != tg || v[i][u].w != tg) {
-                poll_backoff();
+                poll_backoff(a.poll_spin);
                 v[i][u] = ld_ll(rec + off[u]);
               }
             const float ms = __uint_as_float(v[i][2].x), ls = __uint_as_float(v[i][2].z);
@@ -543,7 +554,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           while (v[u].y != tg || v[u].w != tg) {
-            poll_backoff();
+            poll_backoff(a.poll_spin);
             v[u] = ld_ll(src + 2 * (tid + u * M2_CONSUMERS));
           }
           const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&v[u].x));
@@ -593,6 +604,13 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
       // arrive per stage was ~600 cycles per stage)
       for (int s0 = 0; s0 < n_stages; s0 += CH) {
         const int gs = min(CH, n_stages - s0);
+        // Deferred release (see ar_mega3.cuh): the previous group's slots go back to the producer
+        // only now, after the exchange that followed it, so the refill burst of the weight stream
+        // overlaps this group's arithmetic instead of the latency-critical exchange.
+        __syncwarp();
+        if (lane == 0)
+          for (int j = 0; j < rel_n; ++j) mbar_arrive(&empty[int((rel_it + j) % STAGES)]);
+        rel_n = 0;
 #pragma unroll
         for (int j = 0; j < CH; ++j)
           if (j < gs) mbar_wait(&full[int((c_it + j) % STAGES)], uint32_t(((c_it + j) / STAGES) & 1));
@@ -642,13 +660,15 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
 #pragma unroll
           for (int b = 0; b < BT; ++b) acc[j][b] = (aq[0][b] + aq[2][b]) + (aq[1][b] + aq[3][b]);
         }
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (j < gs) mbar_arrive(&empty[int((c_it + j) % STAGES)]);
-        }
+        rel_it = c_it;  // released when the NEXT group of stages starts (see above)
+        rel_n = gs;
         c_it += gs;
+        if (!a.defer) {  // A/B knob (TTS_MEGA_NODEFER=1): hand the slots back at once
+          __syncwarp();
+          if (lane == 0)
+            for (int j = 0; j < rel_n; ++j) mbar_arrive(&empty[int((rel_it + j) % STAGES)]);
+          rel_n = 0;
+        }
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
 #pragma unroll

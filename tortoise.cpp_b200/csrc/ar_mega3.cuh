@@ -155,6 +155,8 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
   const uint32_t tag_base = a.epoch << 8;
   auto tag_of = [&](int layer, int phase) { return tag_base + uint32_t(layer * 8 + phase); };
   long c_it = 0;  // ring stage counter (same order as the producer)
+  long rel_it = 0;  // first stage of the group whose slots are still held
+  int rel_n = 0;
   const int nb = min(a.Bmax, 4);  // candidates the exchange buffers are sized for
   const int nrep = a.nrep;       // replicas in use (<= M2_REP)
   const int rep = cta % nrep;   // the replica this CTA reads
@@ -164,7 +166,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
   auto poll_unit = [&](const uint2 *p, uint32_t tag) -> float2 {
     uint4 v = ld_ll(p);
     while (v.y != tag || v.w != tag) {
-      poll_backoff();
+      poll_backoff(a.poll_spin);
       v = ld_ll(p);
     }
     return make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
@@ -186,7 +188,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           while (v[b][u].y != tag || v[b][u].w != tag) {
-            poll_backoff();
+            poll_backoff(a.poll_spin);
             v[b][u] = ld_ll(buf + size_t(b) * kDim + u * 512 + 2 * tid);
           }
           hv[b][2 * u] = __uint_as_float(v[b][u].x);
@@ -247,7 +249,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
   int S;
   {
     const int cap = max(1, min(4, G / (kHeads * B)));
-    S = min(cap, (n_keys + 31) / 32);
+    S = min(cap, (n_keys + a.keys_per_split - 1) / a.keys_per_split);
     S = max(S, (n_keys + M2_KV_TILE - 1) / M2_KV_TILE);
     S = max(1, min(S, M2_SMAX));
   }
@@ -401,7 +403,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
 #pragma unroll
             for (int u = 0; u < 3; ++u)
               while (v[i][u].y != tg || v[i][u].w != tg) {
-                poll_backoff();
+                poll_backoff(a.poll_spin);
                 v[i][u] = ld_ll(rec + off[u]);
               }
             const float ms = __uint_as_float(v[i][2].x), ls = __uint_as_float(v[i][2].z);
@@ -495,7 +497,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           while (v[u].y != tg || v[u].w != tg) {
-            poll_backoff();
+            poll_backoff(a.poll_spin);
             v[u] = ld_ll(src + 2 * (tid + u * M2_CONSUMERS));
           }
           *reinterpret_cast<uint2 *>(xs + b * M3_XP_K4 + 4 * (tid + u * M2_CONSUMERS)) = make_uint2(v[u].x, v[u].z);
@@ -533,11 +535,99 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
         const int grow0 = s0 * rps, grows = min(gs * rps, rows_cta - grow0);  // rows of this group
         float ep_bias = 0.f;
         if (tid < grows * BT) ep_bias = bias[row0 + grow0 + tid / BT];
+        // Deferred release: the slots of the previous group are handed back to the producer only
+        // now, i.e. AFTER the exchange that followed it.  Released at the end of a GEMV, the
+        // refill burst (148 CTAs x 3-4 stages = 8 MB of TMA traffic) coincides exactly with the
+        // latency-critical (value, tag) exchange and roughly doubles it (tools/xchg_bench.cu:
+        // 3757 -> 5873 cycles per exchange under a saturating stream); released here it overlaps
+        // this group's arithmetic, which reads shared memory only.  (<= 4 pending + <= 4 current
+        // stages never exceed the ring of 8.)
+        __syncwarp();
+        if (lane == 0)
+          for (int j = 0; j < rel_n; ++j) mbar_arrive(&empty[int((rel_it + j) % STAGES)]);
+        rel_n = 0;
         for (int j = 0; j < gs; ++j) {
           const int slot = int((c_it + j) % STAGES);
           mbar_wait(&full[slot], uint32_t(((c_it + j) / STAGES) & 1));
         }
         trace(50);
+        if (BT <= 2 && k4) {
+          // K = 4096 phase (6-8 rows per CTA) on the CUDA cores: with so few rows an m16n8k16 tile
+          // is 5 % useful and HMMA.16816 issues only every ~40 cycles per scheduler on B200 (32 per
+          // warp = ~3100 cycles, profiles/r01_decode_step.md); 4 rows x 32 weights per thread are
+          // ~260 instructions.  Warp w: K quarter w & 3, row parity w >> 2 of each 2-row stage.
+          // The activations (f16-exact, hi plane only) are widened once per phase.
+          const int kq = warp & 3, rsub = warp >> 2;
+          float xr[BT][4][8];
+#pragma unroll
+          for (int b = 0; b < BT; ++b)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = *reinterpret_cast<const uint4 *>(xs + b * M3_XP_K4 + kq * 1024 + q * 256 + lane * 8);
+              const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                xr[b][q][2 * e] = f.x;
+                xr[b][q][2 * e + 1] = f.y;
+              }
+            }
+          uint4 wv[M3_GROUP][4];
+#pragma unroll
+          for (int j = 0; j < M3_GROUP; ++j) {
+            const int r = j * 2 + rsub;
+            const bool valid = j < gs && r < grows;
+            const unsigned char *wp = ring + size_t((c_it + j) % STAGES) * M3_STAGE_SMEM + rsub * M3_PITCH_K4 + kq * 2048 + lane * 16;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) wv[j][q] = valid ? *reinterpret_cast<const uint4 *>(wp + q * 512) : make_uint4(0, 0, 0, 0);
+          }
+          float accf[M3_GROUP][BT];
+#pragma unroll
+          for (int j = 0; j < M3_GROUP; ++j) {
+            float aq[4][BT];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float wf[8];
+              const __half2 *h2 = reinterpret_cast<const __half2 *>(&wv[j][q]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                wf[2 * e] = f.x;
+                wf[2 * e + 1] = f.y;
+              }
+#pragma unroll
+              for (int b = 0; b < BT; ++b) {
+                float t = wf[0] * xr[b][q][0];
+#pragma unroll
+                for (int e = 1; e < 8; ++e) t = fmaf(wf[e], xr[b][q][e], t);
+                aq[q][b] = t;
+              }
+            }
+#pragma unroll
+            for (int b = 0; b < BT; ++b) accf[j][b] = (aq[0][b] + aq[2][b]) + (aq[1][b] + aq[3][b]);
+          }
+          trace(45);
+          rel_it = c_it;
+          rel_n = gs;
+          c_it += gs;
+          if (!a.defer) {
+            __syncwarp();
+            if (lane == 0)
+              for (int j = 0; j < rel_n; ++j) mbar_arrive(&empty[int((rel_it + j) % STAGES)]);
+            rel_n = 0;
+          }
+#pragma unroll
+          for (int j = 0; j < M3_GROUP; ++j)
+#pragma unroll
+            for (int b = 0; b < BT; ++b) {
+              const float v = warp_sum(accf[j][b]);
+              // rows of the other parity get a zero from this warp (the epilogue sums all 8 warps)
+              if (lane == 0) {
+                partial[(warp * 32 + j * 2 + rsub) * BT + b] = v;
+                partial[(warp * 32 + j * 2 + (rsub ^ 1)) * BT + b] = 0.f;
+              }
+            }
+        } else {
         const int mtiles = (grows + 15) >> 4;  // 1 or 2
         uint32_t aaddr[2];
 #pragma unroll
@@ -593,10 +683,15 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
           for (int q = 0; q < 4; ++q) acc[0][q] = (acc[0][q] + acc[1][q]) + (acc[2][q] + acc[3][q]);
         }
         trace(45);
-        __syncwarp();
-        if (lane == 0)
-          for (int j = 0; j < gs; ++j) mbar_arrive(&empty[int((c_it + j) % STAGES)]);
+        rel_it = c_it;  // released when the NEXT group starts (see below)
+        rel_n = gs;
         c_it += gs;
+        if (!a.defer) {  // A/B knob (TTS_MEGA_NODEFER=1): hand the slots back at once
+          __syncwarp();
+          if (lane == 0)
+            for (int j = 0; j < rel_n; ++j) mbar_arrive(&empty[int((rel_it + j) % STAGES)]);
+          rel_n = 0;
+        }
         // hi + lo planes: columns c and c + 4 sit two lanes apart
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
@@ -613,6 +708,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
             }
           }
         }
+        }  // tensor-core path
         trace(46);
         bar_consumers();
         if (s0 == 0) { trace(30 + p); stamp(ph, 2); }
