@@ -179,6 +179,38 @@ def test_fp16_decode_tensor_core_path_vs_cuda_core_path_and_oracle(pkg, golden, 
         assert np.abs(outs["v3"][i] - ref).max() < LOGIT_TOL
 
 
+def test_fp16_decode_long_context_walks_key_tiles(pkg, golden, voice, model_dir):
+    """> 128 and > 256 cached positions: the attention item of the persistent step walks several
+    128-key tiles with running (max, sum, acc).  Checked against the per-op path (TTS_NO_MEGA=1:
+    wsgemv_kernel + ar_attn_decode_kernel, an independent attention implementation on the same f16
+    weights) over a 290-step teacher-forced run; the numpy oracle needs 2.7 s per step."""
+    g = golden("ar_b1.npz")
+    n_steps = 290
+    rs = np.random.RandomState(5)
+    toks = rs.randint(0, 8192, size=n_steps)
+    outs = {}
+    for path in ("mega", "per_op"):
+        if path == "per_op":
+            os.environ["TTS_NO_MEGA"] = "1"
+        try:
+            eng = pkg.Engine(device=0, dtype=pkg.DTYPE_F16, max_batch=1, max_positions=404)
+        finally:
+            os.environ.pop("TTS_NO_MEGA", None)
+        try:
+            eng.load_ar(os.path.join(model_dir, "ggml-model.bin"))
+            eng.ar_prefill(g["tokens"], voice, 1)
+            lgs = []
+            for i in range(n_steps):
+                lgs.append(eng.ar_step([int(toks[i])], 2 + i).copy())
+            outs[path] = np.stack(lgs)
+        finally:
+            eng.close()
+    assert np.isfinite(outs["mega"]).all()
+    err = np.abs(outs["mega"] - outs["per_op"]).reshape(n_steps, -1).max(axis=1)
+    # 18 prefill positions + step + 1 keys: steps 108..112 straddle 128 keys, 236..240 straddle 256
+    assert err.max() < LOGIT_TOL, (int(err.argmax()), float(err.max()))
+
+
 def test_limits_are_errors_not_aborts(engine_f32, golden, voice, pkg):
     g = golden("ar_b1.npz")
     with pytest.raises(pkg.TTSError):

@@ -12,7 +12,7 @@ for B in ((1,) if os.environ.get('B_ONLY') else (1, 2, 4)):
     eng.ar_prefill(g["tokens"], voice, B)
     for i in range(5): eng.ar_step([100]*B, i+2)
     t=[]
-    for i in range(60):
+    for i in range(int(os.environ.get('NSTEP','60'))):
         eng.ar_step([100+i]*B, i+7); t.append(eng.last_stage_ms)
     if os.environ.get('PER_STEP'): print(' '.join(f"{x*1e3:.0f}" for x in t))
     print(f"f16 B={B} decode step median {np.median(t)*1e3:.1f} us min {np.min(t)*1e3:.1f} -> {B/np.median(t)*1e3:.0f} tok/s", flush=True)

@@ -245,29 +245,20 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
   };
 
   // ---------------- attention items -------------------------------------------------------------
+  // One item per (candidate, head), all keys, M2_KV_TILE at a time with running (max, sum, acc).
+  // Splitting the keys of a head over several CTAs costs ~4 us per layer and split level on
+  // B200 (same-box A/B, profiles/r01_decode_keys_per_split_ab.txt: 520 -> 640 us per step when
+  // 64 keys go from one item to two) -- far more than walking the tiles in one CTA.
   const int n_keys = a.n_past + 1;
-  int S;
-  {
-    const int cap = max(1, min(4, G / (kHeads * B)));
-    S = min(cap, (n_keys + a.keys_per_split - 1) / a.keys_per_split);
-    S = max(S, (n_keys + M2_KV_TILE - 1) / M2_KV_TILE);
-    S = max(1, min(S, M2_SMAX));
-  }
-  const int chunk = (n_keys + S - 1) / S;  // <= 128 (host guarantees P <= 1024)
-  const int n_items = B * kHeads * S;
+  const int S = 1;  // records per (candidate, head) in the exchange buffer (the merge below is general)
+  const int n_items = B * kHeads;
+  const int n_tiles = (n_keys + M2_KV_TILE - 1) / M2_KV_TILE;
   const size_t layer_kv = size_t(a.Bmax) * kHeads * a.P * kHeadDim;
-  auto item_range = [&](int item, int &b, int &head, int &s, int &j0, int &j1) {
-    s = item % S;
-    head = (item / S) % kHeads;
-    b = item / (S * kHeads);
-    j0 = min(n_keys, s * chunk);
-    j1 = min(n_keys, j0 + chunk);
-  };
-  // cached rows [j0, min(j1, n_past)) of (b, head) -> shared tiles (cp.async, 16 B per op)
-  auto prefetch_kv = [&](int li, int item) {
-    int b, head, s, j0, j1;
-    item_range(item, b, head, s, j0, j1);
-    const int rows = min(j1, a.n_past) - j0;
+  // cached rows [t * TILE, min((t + 1) * TILE, n_past)) of item (b, head) -> shared tiles (cp.async, 16 B per op)
+  auto prefetch_kv = [&](int li, int item, int t) {
+    const int b = item / kHeads, head = item % kHeads;
+    const int j0 = t * M2_KV_TILE;
+    const int rows = min(j0 + M2_KV_TILE, a.n_past) - j0;
     const __half *K = a.kc + size_t(li) * layer_kv + ((size_t(b) * kHeads + head) * a.P + j0) * kHeadDim;
     const __half *V = a.vc + size_t(li) * layer_kv + ((size_t(b) * kHeads + head) * a.P + j0) * kHeadDim;
     for (int u = tid; u < rows * 8; u += M2_CONSUMERS) {
@@ -277,102 +268,113 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
     }
   };
   auto attention_item = [&](int li, int item, bool prefetched) {
-    int b, head, s, j0, j1;
-    item_range(item, b, head, s, j0, j1);
-    const int c = j1 - j0;
-    const bool has_new = c > 0 && j1 == n_keys;
-    if (!prefetched) prefetch_kv(li, item);
+    const int b = item / kHeads, head = item % kHeads;
     const uint32_t tq = tag_of(li, 1);
     const uint2 *qkv = a.ll_qkv + size_t(b) * 3072;
-    if (tid < 32) {
-      const float2 v = poll_unit(qkv + head * kHeadDim + 2 * tid, tq);
-      qs[2 * tid] = v.x;
-      qs[2 * tid + 1] = v.y;
-    } else if (tid < 64 && has_new) {
-      const int t = tid - 32;
-      const float2 v = poll_unit(qkv + 1024 + head * kHeadDim + 2 * t, tq);
-      *reinterpret_cast<__half2 *>(kt + (c - 1) * M2_KV_LD + 2 * t) = __floats2half2_rn(v.x, v.y);
-    } else if (tid < 96 && has_new) {
-      const int t = tid - 64;
-      const float2 v = poll_unit(qkv + 2048 + head * kHeadDim + 2 * t, tq);
-      *reinterpret_cast<__half2 *>(vt + (c - 1) * M2_KV_LD + 2 * t) = __floats2half2_rn(v.x, v.y);
-    }
-    cp_async_wait_all();
-    bar_consumers();
-    // scores: two threads per key, 32 dims each
-    float lmax = -INFINITY;
-    {
-      const int j = tid >> 1, half = tid & 1;
-      float dot = 0.f;
-      if (j < c) {
-        const uint4 *kr = reinterpret_cast<const uint4 *>(kt + j * M2_KV_LD + half * 32);
-        const float *qh = qs + half * 32;
-        float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const uint4 u = kr[cc];
-          const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = __half22float2(h2[e]);
-            d0 = fmaf(qh[cc * 8 + 2 * e], f.x, d0);
-            d1 = fmaf(qh[cc * 8 + 2 * e + 1], f.y, d1);
-          }
+    float Mr = -INFINITY, Lr = 0.f, orun = 0.f;  // running max / sum (every thread), output dim tid (tid < 64)
+    for (int t = 0; t < n_tiles; ++t) {
+      const int j0 = t * M2_KV_TILE, j1 = min(n_keys, j0 + M2_KV_TILE), c = j1 - j0;
+      const bool has_new = j1 == n_keys;
+      if (t > 0 || !prefetched) prefetch_kv(li, item, t);
+      if (tid < 32) {
+        if (t == 0) {
+          const float2 v = poll_unit(qkv + head * kHeadDim + 2 * tid, tq);
+          qs[2 * tid] = v.x;
+          qs[2 * tid + 1] = v.y;
         }
-        dot = d0 + d1;
+      } else if (tid < 64 && has_new) {
+        const int u = tid - 32;
+        const float2 v = poll_unit(qkv + 1024 + head * kHeadDim + 2 * u, tq);
+        *reinterpret_cast<__half2 *>(kt + (c - 1) * M2_KV_LD + 2 * u) = __floats2half2_rn(v.x, v.y);
+      } else if (tid < 96 && has_new) {
+        const int u = tid - 64;
+        const float2 v = poll_unit(qkv + 2048 + head * kHeadDim + 2 * u, tq);
+        *reinterpret_cast<__half2 *>(vt + (c - 1) * M2_KV_LD + 2 * u) = __floats2half2_rn(v.x, v.y);
       }
-      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-      dot *= 0.125f;
-      if (j < c) {
-        if (half == 0) sc[j] = dot;
-        lmax = dot;
-      }
-    }
-    lmax = warp_max(lmax);
-    if (lane == 0) redf[warp] = lmax;
-    bar_consumers();
-    float mx = redf[0];
+      cp_async_wait_all();
+      bar_consumers();
+      // scores: two threads per key, 32 dims each
+      float lmax = -INFINITY;
+      {
+        const int j = tid >> 1, half = tid & 1;
+        float dot = 0.f;
+        if (j < c) {
+          const uint4 *kr = reinterpret_cast<const uint4 *>(kt + j * M2_KV_LD + half * 32);
+          const float *qh = qs + half * 32;
+          float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-    for (int w = 1; w < GV_WARPS; ++w) mx = fmaxf(mx, redf[w]);
-    float lsum = 0.f;
-    if (tid < c) {
-      const float p = expf(sc[tid] - mx);
-      sc[tid] = p;
-      lsum = p;
-    }
-    lsum = warp_sum(lsum);
-    if (lane == 0) redf[8 + warp] = lsum;
-    bar_consumers();
-    // unnormalised output: lane = dim pair, warp = key partition
-    {
-      float o0 = 0.f, o1 = 0.f;
-      for (int j = warp; j < c; j += GV_WARPS) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(vt + j * M2_KV_LD + 2 * lane));
-        const float p = sc[j];
-        o0 = fmaf(p, f.x, o0);
-        o1 = fmaf(p, f.y, o1);
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint4 u = kr[cc];
+            const __half2 *h2 = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(h2[e]);
+              d0 = fmaf(qh[cc * 8 + 2 * e], f.x, d0);
+              d1 = fmaf(qh[cc * 8 + 2 * e + 1], f.y, d1);
+            }
+          }
+          dot = d0 + d1;
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot *= 0.125f;
+        if (j < c) {
+          if (half == 0) sc[j] = dot;
+          lmax = dot;
+        }
       }
-      pp[warp * 64 + 2 * lane] = o0;
-      pp[warp * 64 + 2 * lane + 1] = o1;
+      lmax = warp_max(lmax);
+      if (lane == 0) redf[warp] = lmax;
+      bar_consumers();
+      float mx = redf[0];
+#pragma unroll
+      for (int w = 1; w < GV_WARPS; ++w) mx = fmaxf(mx, redf[w]);
+      float lsum = 0.f;
+      if (tid < c) {
+        const float p = expf(sc[tid] - mx);
+        sc[tid] = p;
+        lsum = p;
+      }
+      lsum = warp_sum(lsum);
+      if (lane == 0) redf[8 + warp] = lsum;
+      bar_consumers();
+      // unnormalised output of the tile: lane = dim pair, warp = key partition
+      {
+        float o0 = 0.f, o1 = 0.f;
+        for (int j = warp; j < c; j += GV_WARPS) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(vt + j * M2_KV_LD + 2 * lane));
+          const float p = sc[j];
+          o0 = fmaf(p, f.x, o0);
+          o1 = fmaf(p, f.y, o1);
+        }
+        pp[warp * 64 + 2 * lane] = o0;
+        pp[warp * 64 + 2 * lane + 1] = o1;
+      }
+      bar_consumers();
+      // fold the tile into the running statistics (exp(-inf) = 0 on the first tile)
+      {
+        float ts = 0.f;
+#pragma unroll
+        for (int w = 0; w < GV_WARPS; ++w) ts += redf[8 + w];
+        const float nM = fmaxf(Mr, mx);
+        const float so = expf(Mr - nM), sn = expf(mx - nM);
+        if (tid < 64) {
+          float o = 0.f;
+#pragma unroll
+          for (int w = 0; w < GV_WARPS; ++w) o += pp[w * 64 + tid];
+          orun = orun * so + o * sn;
+        }
+        Lr = Lr * so + ts * sn;
+        Mr = nM;
+      }
+      // (the next tile / item starts with loads into kt/vt and writes sc/pp/redf: separate them from the reads above)
+      bar_consumers();
     }
-    bar_consumers();
-    uint2 *rec = a.ll_att + (size_t(b * kHeads + head) * M2_SMAX + s) * M2_REC;
+    uint2 *rec = a.ll_att + size_t(b * kHeads + head) * M2_SMAX * M2_REC;
     const uint32_t to = tag_of(li, 2);
     if (tid < 66) {
-      float o = 0.f;
-      if (tid < 64) {
-#pragma unroll
-        for (int w = 0; w < GV_WARPS; ++w) o += pp[w * 64 + tid];
-      } else if (tid == 64) {
-        o = c > 0 ? mx : -INFINITY;
-      } else {
-#pragma unroll
-        for (int w = 0; w < GV_WARPS; ++w) o += redf[8 + w];
-      }
+      const float o = tid < 64 ? orun : (tid == 64 ? Mr : Lr);
       for (int r = 0; r < nrep; ++r) st_ll(rec + r * att_rep + tid, o, to);
     }
-    // (the next item of this CTA, if any, starts with loads into kt/vt: separate them from the reads above)
-    bar_consumers();
   };
   // merge the S partials of every (candidate, head): thread t -> head t/16, dims 4 (t%16) .. +3.
   // Splits are fetched four at a time (all loads in flight before the first tag check) and folded
@@ -441,7 +443,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
     stamp(ph, 0);
     // ---------------- prologue ----------------
     if (p == 0 || p == 2) {
-      if (p == 0 && !tail && cta < n_items) prefetch_kv(li, cta);  // lands while the QKV phase runs
+      if (p == 0 && !tail && cta < n_items) prefetch_kv(li, cta, 0);  // lands while the QKV phase runs
       load_ln(tail ? a.lnf_w : (p == 0 ? l.ln1_w : l.ln2_w), tail ? a.lnf_b : (p == 0 ? l.ln1_b : l.ln2_b), lw, lb);
       if (ph == 0) {  // h = mel_emb[tok] + mel_pos[pos]   (main.cpp:2676-2691)
 #pragma unroll
