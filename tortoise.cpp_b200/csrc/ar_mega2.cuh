@@ -3,7 +3,7 @@
 //
 // Same math as ar_mega.cuh / wsgemv.cuh (reference graph autoregressive_graph(fake_inputs=false),
 // main.cpp:2668-3029).  What changed, and why (measured with the in-kernel clock trace,
-// profiles/r01b_mega_trace.md): in the first generation a phase boundary cost 3000-4500 cycles
+// profiles/r01_decode_step.md): in the first generation a phase boundary cost 3000-4500 cycles
 // (bar.sync -> MEMBAR.GPU + RED -> one thread polling the counter -> bar.sync -> the L2 round trip
 // that finally fetches the activations) and the LayerNorm prologue another 3000 (two more dependent
 // L2 round trips).  Here

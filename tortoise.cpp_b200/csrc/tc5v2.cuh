@@ -5,7 +5,7 @@
 // `taps` shifted K passes, f32 accumulation in TMEM, fused epilogue).  What changed, and why:
 //   * the first-generation kernel (128 x 32 tiles, cp.async loaders) re-read every A tile from
 //     32 CTAs at once: ~120 MB of L2->SM traffic per 3-tap convolution, served at ~3 TB/s
-//     (profiles/r01_tc5_ncu_full.md) -- 4x under both the L2 and the per-SM LSU limits, i.e.
+//     (profiles/r01d_tc5v2_ncu_full_raw.csv) -- 4x under both the L2 and the per-SM LSU limits, i.e.
 //     bound by the same few L2 lines being hammered by every CTA.  128 x 128 tiles cut the
 //     traffic 2.5x; the lost parallelism (32 tiles for the [382 x 1024] problems of the
 //     denoiser) comes back as split-K: `csz` CTAs of one cluster (1,1,csz) each accumulate a
@@ -224,7 +224,7 @@ static __global__ void __launch_bounds__(T6_THREADS, 1)
     double gs1 = 0.0, gs2 = 0.0;
     // Two rows per warp and pass, every load of the pass in flight before the first use (2 x csz
     // distributed-shared-memory reads + 2 residual reads): the pass costs one DSMEM round trip
-    // instead of csz dependent ones (the reduction was 3 us of a 9 us kernel, profiles/r01_tc5_trace.md).
+    // instead of csz dependent ones (the reduction was 3 us of a 9 us kernel, profiles/r01d_tc5v2_timeline.txt).
     for (int rr0 = warp * 2; rr0 < rows_per; rr0 += 16) {
       float4 part[2][8], o4[2];
       bool live[2];
