@@ -40,6 +40,9 @@ constexpr int T6_PLANE = 128 * 128;        // bytes of one 128-row x 64-half swi
 constexpr int T6_RED_LD = T6_BN + 4;       // padded row of the f32 partial tile (conflict-free both ways)
 constexpr int T6_CTRL = 1024;              // barriers + tmem slot + GN scratch
 constexpr int T6_MAX_STAGES = 8;
+#ifndef T6_MIN_CTAS
+#define T6_MIN_CTAS 1  // 2 = register budget for two co-resident CTAs (experiment below: no gain)
+#endif
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
   asm volatile(
@@ -62,7 +65,7 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank
   return v;
 }
 
-static __global__ void __launch_bounds__(T6_THREADS, 1)
+static __global__ void __launch_bounds__(T6_THREADS, T6_MIN_CTAS)
     tc5v2_kernel(TGemmArgs g, const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                  const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, int csz,
                  int stages) {
@@ -391,7 +394,17 @@ static inline int launch_tc5v2(const Launcher &L, TGemmArgs g) {
   if (!want_gn) g.gn_partial = nullptr;
   g.gn_mtiles = mt * csz;
   const size_t stage_bytes = size_t(T6_PLANE) * ((alo ? 2 : 1) + (wlo ? 2 : 1));
-  const size_t budget = 226 * 1024 - 1024 - T6_CTRL;
+  size_t budget = 226 * 1024 - 1024 - T6_CTRL;
+  {
+    // Experiment knob (default off): cap the ring so two CTAs fit on an SM (with -DT6_MIN_CTAS=2 for
+    // the registers) and the next kernel of the chain can become resident under programmatic
+    // dependent launch.  Measured, 20 sampling steps on one box: 30.4 ms uncapped, 30.7 ms at 100 KB,
+    // 31.5 ms at 72 KB, 29.6 ms at 100 KB without PDL -- residency is not what serialises the chain.
+    static long cap_kb = -1;
+    if (cap_kb < 0) { const char *e = getenv("TTS_TC5_SMEM_KB"); cap_kb = e ? atol(e) : 0; }
+    const size_t cap = size_t(cap_kb) * 1024;
+    if (cap > 0 && cap / stage_bytes >= 2 && cap >= size_t(T6_BM) * T6_RED_LD * 4) budget = std::min(budget, cap);
+  }
   int stages = int(budget / stage_bytes);
   if (stages > T6_MAX_STAGES) stages = T6_MAX_STAGES;
   const int per_rank = (iters + csz - 1) / csz;
