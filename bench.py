@@ -186,6 +186,21 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def stage_hbm(sm_ar_ms, diff_ms, voc_ms, n_dec, step_bytes, peak):
+    """Per-stage achieved GB/s = bytes the stage must stream at least once per pass / device time.
+    AR: decode steps x bytes of one step (prefill and the latent pass add their own weight pass each);
+    diffusion: 180.48 M params as f16 conv / split-f16 matmul operands (0.361 GB) per sampling step;
+    vocoder: 14.79 M params as f16 (29.6 MB) per utterance."""
+    ar_bytes = (n_dec + 2) * step_bytes
+    diff_bytes = DIFF_STEPS * 180.48e6 * 2
+    voc_bytes = 14.79e6 * 2
+    out = {}
+    for name, by, ms in (("ar", ar_bytes, sm_ar_ms), ("diffusion", diff_bytes, diff_ms), ("vocoder", voc_bytes, voc_ms)):
+        gbs = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        out[name] = {"GBs": gbs, "frac": gbs / peak, "device_ms": ms}
+    return out
+
+
 def workload_config(world):
     return {"workload": "configs[1]: 1 candidate/GPU, prompt 'this is a test message.' (T=16), voice mol.bin, "
                         f"{N_CODES} mel codes forced, {DIFF_STEPS} diffusion steps, full AR+diffusion+vocoder",
@@ -327,6 +342,10 @@ def main():
         "ar_mel_tokens_per_s": tok_total / ar_wall, "ar_mel_tokens_per_s_device": tok_total / (ar_dev_ms * args.steps / 1e3) if world == 1 else None,
         "stage_ms": {"ar_wall": ar_wall / args.steps * 1e3, "ar_device": ar_dev_ms, "diffusion_device": diff_ms / args.steps,
                      "vocoder_device": voc_ms / args.steps},
+        # achieved fraction of the HBM roofline per stage (north star): algorithmic weight bytes of the stage
+        # (each decode step / sampling step / vocoder pass streams its weights once) over device time
+        "stage_hbm": stage_hbm(sm_ar_ms=ar_dev_ms, diff_ms=diff_ms / args.steps, voc_ms=voc_ms / args.steps,
+                               n_dec=n_tokens / args.steps, step_bytes=step_bytes, peak=peak),
         "e2e": {"value": audio_total / wall, "unit": "audio-s/wall-s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": sampler.summary(),

@@ -328,6 +328,9 @@ static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
     static int kps = -1;
     if (kps < 0) { const char *e = getenv("TTS_MEGA_KPS"); kps = e ? std::max(8, std::min(128, atoi(e))) : 128; }
     a.keys_per_split = kps;
+    static int ef = -1;
+    if (ef < 0) { const char *e = getenv("TTS_MEGA_NOEVICT"); ef = (e && e[0] == '0') ? 1 : 0; }  // TTS_MEGA_NOEVICT=0 turns the hint ON; same-box A/B: 541 us with, 527 us without
+    a.evict_first = ef;
   }
   if (sizeof(WT) == 2 && !c->use_mega_v2) {
     if (B == 1) launch_mega3_bt<1>(c, a);

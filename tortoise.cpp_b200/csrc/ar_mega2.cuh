@@ -61,6 +61,7 @@ struct Mega2Args {
   unsigned int epoch;  // unique per launch (1 .. 2^24-1)
   long long *dbg;      // optional clock trace (TTS_MEGA_TRACE=1: CTA 0, cycle stamps; =2: every CTA, 4 globaltimer stamps per phase)
   int dbg_mode;
+  int evict_first;  // 1: weight stream with the L2 evict-first hint (TTS_MEGA_NOEVICT=1 turns it off)
   int keys_per_split;  // attention: keys per (candidate, head) item before splitting (TTS_MEGA_KPS)
   int poll_spin;  // cycles between two polls of a missing tag (TTS_MEGA_SPIN)
   int defer;  // 1: deferred ring-slot release (default)
@@ -187,6 +188,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(M2_PRODUCER_REGS));
     // ---------------- weight stream: every slice of the step, in consumption order ------------
     if (warp == M2_CONSUMERS / 32 && lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();  // see ar_mega3.cuh
       long it = 0;
       for (int sid = 0; sid <= 120; ++sid) {
         int N, K, row0, rows;
@@ -201,7 +203,8 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
           mbar_wait(&empty[slot], uint32_t((it / STAGES) & 1) ^ 1u);
           const uint32_t bytes = uint32_t(min(size_t(GV_STAGE_BYTES), total - off));
           mbar_arrive_expect_tx(&full[slot], bytes);
-          bulk_g2s(ring + size_t(slot) * GV_STAGE_BYTES, src + off, bytes, &full[slot]);
+          if (a.evict_first) bulk_g2s_hint(ring + size_t(slot) * GV_STAGE_BYTES, src + off, bytes, &full[slot], pol);
+          else bulk_g2s(ring + size_t(slot) * GV_STAGE_BYTES, src + off, bytes, &full[slot]);
         }
       }
     }
@@ -240,23 +243,32 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
 
   // thread t owns elements {2t, 2t+1, 512+2t, 512+2t+1} of a 1024-vector
   float hv[BT][4];
+  // Every pending unit is re-requested in the SAME round: polling unit after unit costs one extra
+  // L2 round trip (~0.35 us) per unit after the previous one has arrived, because the first load
+  // of every unit is issued before any producer has stored.
   auto poll_h = [&](const uint2 *buf, uint32_t tag) {
     uint4 v[BT][2];
 #pragma unroll
     for (int b = 0; b < BT; ++b)
-      if (b < B) {
-        v[b][0] = ld_ll(buf + size_t(b) * kDim + 2 * tid);
-        v[b][1] = ld_ll(buf + size_t(b) * kDim + 512 + 2 * tid);
-      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) v[b][u] = make_uint4(0, ~tag, 0, ~tag);
+    for (;;) {
+      bool pending = false;
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (b < B && (v[b][u].y != tag || v[b][u].w != tag)) {
+            v[b][u] = ld_ll(buf + size_t(b) * kDim + u * 512 + 2 * tid);
+            pending = true;
+          }
+      if (!pending) break;
+    }
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
       if (b < B) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          while (v[b][u].y != tag || v[b][u].w != tag) {
-            poll_backoff(a.poll_spin);
-            v[b][u] = ld_ll(buf + size_t(b) * kDim + u * 512 + 2 * tid);
-          }
           hv[b][2 * u] = __uint_as_float(v[b][u].x);
           hv[b][2 * u + 1] = __uint_as_float(v[b][u].z);
         }
@@ -442,51 +454,39 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
       for (int r = 0; r < nrep; ++r) st_ll(rec + r * att_rep + tid, o, to);
     }
   };
-  // merge the S partials of every (candidate, head): thread t -> head t/16, dims 4 (t%16) .. +3.
-  // Splits are fetched four at a time (all loads in flight before the first tag check) and folded
-  // with the running-maximum form of the log-sum-exp merge.
+  // normalise the attention output of every (candidate, head): thread t -> head t/16, dims 4 (t%16) .. +3
   auto attention_merge = [&](int li) {
     const uint32_t tg = tag_of(li, 2);
     const int head = tid >> 4, d0 = (tid & 15) * 4;
+    // one record per (candidate, head): {acc[64], max, sum}; this thread needs 4 acc values and the
+    // sum (softmax-normalised output = acc / sum; the max only matters when records are merged).
+    // All pending units of all candidates are re-requested in the same round (see poll_h).
+    uint4 v[BT][3];
+#pragma unroll
+    for (int b = 0; b < BT; ++b)
+#pragma unroll
+      for (int u = 0; u < 3; ++u) v[b][u] = make_uint4(0, ~tg, 0, ~tg);
+    for (;;) {
+      bool pending = false;
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const uint2 *rec = a.ll_att + rep * att_rep + size_t(b * kHeads + head) * M2_SMAX * M2_REC;
+        const int off[3] = {d0, d0 + 2, 64};
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (b < B && (v[b][u].y != tg || v[b][u].w != tg)) {
+            v[b][u] = ld_ll(rec + off[u]);
+            pending = true;
+          }
+      }
+      if (!pending) break;
+    }
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
       if (b >= B) break;
-      const uint2 *base = a.ll_att + rep * att_rep + size_t(b * kHeads + head) * M2_SMAX * M2_REC;
-      float M = -INFINITY, L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int s0 = 0; s0 < S; s0 += 4) {
-        uint4 v[4][3];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (s0 + i < S) {
-            const uint2 *rec = base + size_t(s0 + i) * M2_REC;
-            v[i][0] = ld_ll(rec + d0);
-            v[i][1] = ld_ll(rec + d0 + 2);
-            v[i][2] = ld_ll(rec + 64);
-          }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (s0 + i < S) {
-            const uint2 *rec = base + size_t(s0 + i) * M2_REC;
-            const int off[3] = {d0, d0 + 2, 64};
-#pragma unroll
-            for (int u = 0; u < 3; ++u)
-              while (v[i][u].y != tg || v[i][u].w != tg) {
-                poll_backoff(a.poll_spin);
-                v[i][u] = ld_ll(rec + off[u]);
-              }
-            const float ms = __uint_as_float(v[i][2].x), ls = __uint_as_float(v[i][2].z);
-            if (ms != -INFINITY) {  // (an empty key range contributes nothing)
-              const float nM = fmaxf(M, ms);
-              const float sc_old = expf(M - nM), w = expf(ms - nM);  // exp(-inf) = 0 on the first split
-              L = L * sc_old + w * ls;
-              o[0] = o[0] * sc_old + w * __uint_as_float(v[i][0].x);
-              o[1] = o[1] * sc_old + w * __uint_as_float(v[i][0].z);
-              o[2] = o[2] * sc_old + w * __uint_as_float(v[i][1].x);
-              o[3] = o[3] * sc_old + w * __uint_as_float(v[i][1].z);
-              M = nM;
-            }
-          }
-      }
+      const float o[4] = {__uint_as_float(v[b][0].x), __uint_as_float(v[b][0].z), __uint_as_float(v[b][1].x),
+                          __uint_as_float(v[b][1].z)};
+      const float L = __uint_as_float(v[b][2].z);
       const float inv = 1.0f / L;
       *reinterpret_cast<float4 *>(xin + b * kFF + head * kHeadDim + d0) =
           make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
@@ -552,13 +552,19 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
         const uint2 *src = a.ll_m + rep * m_rep + size_t(b) * (kFF / 2);
         uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld_ll(src + 2 * (tid + u * M2_CONSUMERS));
+        for (int u = 0; u < 4; ++u) v[u] = make_uint4(0, ~tg, 0, ~tg);
+        for (;;) {  // all pending units per round (see poll_h)
+          bool pending = false;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (v[u].y != tg || v[u].w != tg) {
+              v[u] = ld_ll(src + 2 * (tid + u * M2_CONSUMERS));
+              pending = true;
+            }
+          if (!pending) break;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          while (v[u].y != tg || v[u].w != tg) {
-            poll_backoff(a.poll_spin);
-            v[u] = ld_ll(src + 2 * (tid + u * M2_CONSUMERS));
-          }
           const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&v[u].x));
           const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&v[u].z));
           *reinterpret_cast<float4 *>(xin + b * kFF + 4 * (tid + u * M2_CONSUMERS)) = make_float4(f0.x, f0.y, f1.x, f1.y);

@@ -121,6 +121,9 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(M2_PRODUCER_REGS));
     // ---------------- weight stream: every slice of the step, in consumption order ------------
     if (warp == M2_CONSUMERS / 32 && lane == 0) {
+      // 0.77 GB of weights stream through a 126 MB L2 every step: evict-first keeps them from
+      // displacing the (value, tag) exchange lines, whose misses show up as sporadic 2-3 us phases
+      const uint64_t pol = l2_policy_evict_first();
       long it = 0;
       for (int sid = 0; sid <= 120; ++sid) {
         int N, K, row0, rows;
@@ -134,8 +137,11 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
           const int slot = int(it % STAGES), nr = min(rps, rows - r0);
           mbar_wait(&empty[slot], uint32_t((it / STAGES) & 1) ^ 1u);
           mbar_arrive_expect_tx(&full[slot], uint32_t(nr) * row_bytes);
-          for (int r = 0; r < nr; ++r)
-            bulk_g2s(ring + size_t(slot) * M3_STAGE_SMEM + r * pitch, src + size_t(r0 + r) * row_bytes, row_bytes, &full[slot]);
+          for (int r = 0; r < nr; ++r) {
+            void *dst = ring + size_t(slot) * M3_STAGE_SMEM + r * pitch;
+            if (a.evict_first) bulk_g2s_hint(dst, src + size_t(r0 + r) * row_bytes, row_bytes, &full[slot], pol);
+            else bulk_g2s(dst, src + size_t(r0 + r) * row_bytes, row_bytes, &full[slot]);
+          }
         }
       }
     }
@@ -174,23 +180,32 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
 
   // thread t owns elements {2t, 2t+1, 512+2t, 512+2t+1} of a 1024-vector
   float hv[BT][4];
+  // Every pending unit is re-requested in the SAME round: polling unit after unit costs one extra
+  // L2 round trip (~0.35 us) per unit after the previous one has arrived, because the first load
+  // of every unit is issued before any producer has stored.
   auto poll_h = [&](const uint2 *buf, uint32_t tag) {
     uint4 v[BT][2];
 #pragma unroll
     for (int b = 0; b < BT; ++b)
-      if (b < B) {
-        v[b][0] = ld_ll(buf + size_t(b) * kDim + 2 * tid);
-        v[b][1] = ld_ll(buf + size_t(b) * kDim + 512 + 2 * tid);
-      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) v[b][u] = make_uint4(0, ~tag, 0, ~tag);
+    for (;;) {
+      bool pending = false;
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (b < B && (v[b][u].y != tag || v[b][u].w != tag)) {
+            v[b][u] = ld_ll(buf + size_t(b) * kDim + u * 512 + 2 * tid);
+            pending = true;
+          }
+      if (!pending) break;
+    }
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
       if (b < B) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          while (v[b][u].y != tag || v[b][u].w != tag) {
-            poll_backoff(a.poll_spin);
-            v[b][u] = ld_ll(buf + size_t(b) * kDim + u * 512 + 2 * tid);
-          }
           hv[b][2 * u] = __uint_as_float(v[b][u].x);
           hv[b][2 * u + 1] = __uint_as_float(v[b][u].z);
         }
@@ -376,51 +391,39 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
       for (int r = 0; r < nrep; ++r) st_ll(rec + r * att_rep + tid, o, to);
     }
   };
-  // merge the S partials of every (candidate, head): thread t -> head t/16, dims 4 (t%16) .. +3.
-  // Splits are fetched four at a time (all loads in flight before the first tag check) and folded
-  // with the running-maximum form of the log-sum-exp merge.
+  // normalise the attention output of every (candidate, head): thread t -> head t/16, dims 4 (t%16) .. +3
   auto attention_merge = [&](int li) {
     const uint32_t tg = tag_of(li, 2);
     const int head = tid >> 4, d0 = (tid & 15) * 4;
+    // one record per (candidate, head): {acc[64], max, sum}; this thread needs 4 acc values and the
+    // sum (softmax-normalised output = acc / sum; the max only matters when records are merged).
+    // All pending units of all candidates are re-requested in the same round (see poll_h).
+    uint4 v[BT][3];
+#pragma unroll
+    for (int b = 0; b < BT; ++b)
+#pragma unroll
+      for (int u = 0; u < 3; ++u) v[b][u] = make_uint4(0, ~tg, 0, ~tg);
+    for (;;) {
+      bool pending = false;
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const uint2 *rec = a.ll_att + rep * att_rep + size_t(b * kHeads + head) * M2_SMAX * M2_REC;
+        const int off[3] = {d0, d0 + 2, 64};
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (b < B && (v[b][u].y != tg || v[b][u].w != tg)) {
+            v[b][u] = ld_ll(rec + off[u]);
+            pending = true;
+          }
+      }
+      if (!pending) break;
+    }
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
       if (b >= B) break;
-      const uint2 *base = a.ll_att + rep * att_rep + size_t(b * kHeads + head) * M2_SMAX * M2_REC;
-      float M = -INFINITY, L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int s0 = 0; s0 < S; s0 += 4) {
-        uint4 v[4][3];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (s0 + i < S) {
-            const uint2 *rec = base + size_t(s0 + i) * M2_REC;
-            v[i][0] = ld_ll(rec + d0);
-            v[i][1] = ld_ll(rec + d0 + 2);
-            v[i][2] = ld_ll(rec + 64);
-          }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (s0 + i < S) {
-            const uint2 *rec = base + size_t(s0 + i) * M2_REC;
-            const int off[3] = {d0, d0 + 2, 64};
-#pragma unroll
-            for (int u = 0; u < 3; ++u)
-              while (v[i][u].y != tg || v[i][u].w != tg) {
-                poll_backoff(a.poll_spin);
-                v[i][u] = ld_ll(rec + off[u]);
-              }
-            const float ms = __uint_as_float(v[i][2].x), ls = __uint_as_float(v[i][2].z);
-            if (ms != -INFINITY) {  // (an empty key range contributes nothing)
-              const float nM = fmaxf(M, ms);
-              const float sc_old = expf(M - nM), w = expf(ms - nM);  // exp(-inf) = 0 on the first split
-              L = L * sc_old + w * ls;
-              o[0] = o[0] * sc_old + w * __uint_as_float(v[i][0].x);
-              o[1] = o[1] * sc_old + w * __uint_as_float(v[i][0].z);
-              o[2] = o[2] * sc_old + w * __uint_as_float(v[i][1].x);
-              o[3] = o[3] * sc_old + w * __uint_as_float(v[i][1].z);
-              M = nM;
-            }
-          }
-      }
+      const float o[4] = {__uint_as_float(v[b][0].x), __uint_as_float(v[b][0].z), __uint_as_float(v[b][1].x),
+                          __uint_as_float(v[b][1].z)};
+      const float L = __uint_as_float(v[b][2].z);
       const float inv = 1.0f / L;
       __half2 h0, l0, h1, l1;
       split16(o[0] * inv, o[1] * inv, h0, l0);
@@ -495,13 +498,19 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
         const uint2 *src = a.ll_m + rep * m_rep + size_t(b) * (kFF / 2);
         uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld_ll(src + 2 * (tid + u * M2_CONSUMERS));
+        for (int u = 0; u < 4; ++u) v[u] = make_uint4(0, ~tg, 0, ~tg);
+        for (;;) {  // all pending units per round (see poll_h)
+          bool pending = false;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (v[u].y != tg || v[u].w != tg) {
+              v[u] = ld_ll(src + 2 * (tid + u * M2_CONSUMERS));
+              pending = true;
+            }
+          if (!pending) break;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          while (v[u].y != tg || v[u].w != tg) {
-            poll_backoff(a.poll_spin);
-            v[u] = ld_ll(src + 2 * (tid + u * M2_CONSUMERS));
-          }
           *reinterpret_cast<uint2 *>(xs + b * M3_XP_K4 + 4 * (tid + u * M2_CONSUMERS)) = make_uint2(v[u].x, v[u].z);
         }
       }

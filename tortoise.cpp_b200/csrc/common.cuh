@@ -134,6 +134,22 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
       : "memory");
 }
 
+// same with an L2 eviction-priority hint (createpolicy): streamed-once data must not displace the
+// small hot working set (exchange buffers, KV cache) from L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 // ---- small math helpers matching the reference's CPU numerics ----------------------------
 // fp16 round trip (ggml_cpy F32->F16->F32, main.cpp:2789-2790; round-to-nearest-even)
 __device__ __forceinline__ float h16(float x) { return __half2float(__float2half_rn(x)); }
