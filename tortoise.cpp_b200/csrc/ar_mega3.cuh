@@ -82,12 +82,21 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
   // the layer table (pointers) lives in shared memory: a pointer fetched from global memory in
   // front of every dependent load stalls the in-order issue for an L2 round trip
   __shared__ MegaLayer s_layers[kLayers];
+  __shared__ int s_slice[4][2];  // {row0, rows} of this CTA for N = 3072, 1024, 4096, 8194
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
   const int B = a.B;
   for (int i = tid; i < int(kLayers * sizeof(MegaLayer) / 8); i += M2_THREADS)
     reinterpret_cast<unsigned long long *>(s_layers)[i] = reinterpret_cast<const unsigned long long *>(a.layers)[i];
+  if (tid < 4) {
+    // the c_fc slices start and end on even rows (its outputs are exchanged as half2 pairs)
+    const int N = tid == 0 ? 3072 : (tid == 1 ? kDim : (tid == 2 ? kFF : kMelVocab));
+    const int gran = N == kFF ? 2 : 1;
+    const int U = N / gran, base = U / G, rem = U % G;
+    s_slice[tid][1] = gran * (base + (cta < rem ? 1 : 0));
+    s_slice[tid][0] = gran * (cta * base + min(cta, rem));
+  }
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -108,13 +117,11 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
       default: N = kDim; K = kFF; W = l.w_proj2; break;
     }
   };
-  // rows of a matrix owned by this CTA; the c_fc slices start and end on even rows (its outputs
-  // are exchanged as half2 pairs)
+  // rows of a matrix owned by this CTA (table filled before the role split)
   auto slice = [&](int N, int &row0, int &rows) {
-    const int gran = N == kFF ? 2 : 1;
-    const int U = N / gran, base = U / G, rem = U % G;
-    rows = gran * (base + (cta < rem ? 1 : 0));
-    row0 = gran * (cta * base + min(cta, rem));
+    const int i = N == 3072 ? 0 : (N == kDim ? 1 : (N == kFF ? 2 : 3));
+    row0 = s_slice[i][0];
+    rows = s_slice[i][1];
   };
 
   if (warp >= M2_CONSUMERS / 32) {
@@ -160,8 +167,9 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
   };
   const uint32_t tag_base = a.epoch << 8;
   auto tag_of = [&](int layer, int phase) { return tag_base + uint32_t(layer * 8 + phase); };
-  long c_it = 0;  // ring stage counter (same order as the producer)
-  long rel_it = 0;  // first stage of the group whose slots are still held
+  static_assert((M3_STAGES & (M3_STAGES - 1)) == 0, "slot = counter & (STAGES - 1)");
+  uint32_t c_it = 0;    // ring stage counter (same order as the producer)
+  uint32_t rel_it = 0;  // first stage of the group whose slots are still held
   int rel_n = 0;
   const int nb = min(a.Bmax, 4);  // candidates the exchange buffers are sized for
   const int nrep = a.nrep;       // replicas in use (<= M2_REP)
@@ -532,7 +540,8 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
       const int kbase = warp * ksteps * 16;
       int row0, rows_cta;
       slice(N, row0, rows_cta);
-      const int n_stages = (rows_cta + rps - 1) / rps;
+      const int rlog = k4 ? 1 : 3;  // log2(rps): no runtime division in a phase
+      const int n_stages = (rows_cta + rps - 1) >> rlog;
       // B fragment source: column n = lane / 4 of the n = 8 tile -> plane row (hi: n < 4, lo: n >= 4)
       const int ncol = lane >> 2;
       const int cand = ncol & 3;
@@ -555,11 +564,16 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
         // stages never exceed the ring of 8.)
         __syncwarp();
         if (lane == 0)
-          for (int j = 0; j < rel_n; ++j) mbar_arrive(&empty[int((rel_it + j) % STAGES)]);
+          for (int j = 0; j < rel_n; ++j) mbar_arrive(&empty[(rel_it + j) & (STAGES - 1)]);
         rel_n = 0;
-        for (int j = 0; j < gs; ++j) {
-          const int slot = int((c_it + j) % STAGES);
-          mbar_wait(&full[slot], uint32_t(((c_it + j) / STAGES) & 1));
+        // the (up to 4) stage barriers are probed together: four blocking try_wait in a row cost
+        // ~90 cycles each even when the stages landed long ago
+        for (;;) {
+          bool ok = true;
+#pragma unroll
+          for (int j = 0; j < M3_GROUP; ++j)
+            if (j < gs) ok = mbar_test_wait(&full[(c_it + j) & (STAGES - 1)], ((c_it + j) / STAGES) & 1u) && ok;
+          if (ok) break;
         }
         trace(50);
         if (BT <= 2 && k4) {
@@ -588,7 +602,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
           for (int j = 0; j < M3_GROUP; ++j) {
             const int r = j * 2 + rsub;
             const bool valid = j < gs && r < grows;
-            const unsigned char *wp = ring + size_t((c_it + j) % STAGES) * M3_STAGE_SMEM + rsub * M3_PITCH_K4 + kq * 2048 + lane * 16;
+            const unsigned char *wp = ring + ((c_it + j) & (STAGES - 1)) * M3_STAGE_SMEM + rsub * M3_PITCH_K4 + kq * 2048 + lane * 16;
 #pragma unroll
             for (int q = 0; q < 4; ++q) wv[j][q] = valid ? *reinterpret_cast<const uint4 *>(wp + q * 512) : make_uint4(0, 0, 0, 0);
           }
@@ -624,7 +638,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
           if (!a.defer) {
             __syncwarp();
             if (lane == 0)
-              for (int j = 0; j < rel_n; ++j) mbar_arrive(&empty[int((rel_it + j) % STAGES)]);
+              for (int j = 0; j < rel_n; ++j) mbar_arrive(&empty[(rel_it + j) & (STAGES - 1)]);
             rel_n = 0;
           }
 #pragma unroll
@@ -645,8 +659,8 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
         for (int mt = 0; mt < 2; ++mt) {
           int gr = mt * 16 + a_row;
           if (gr >= grows) gr = 0;  // rows past the slice: any resident row (results unused)
-          const int slot = int((c_it + gr / rps) % STAGES);
-          aaddr[mt] = smem_u32(ring) + uint32_t(slot * M3_STAGE_SMEM + (gr % rps) * pitch + (kbase + a_kofs) * 2);
+          const int slot = int((c_it + uint32_t(gr >> rlog)) & (STAGES - 1));
+          aaddr[mt] = smem_u32(ring) + uint32_t(slot * M3_STAGE_SMEM + (gr & (rps - 1)) * pitch + (kbase + a_kofs) * 2);
         }
         // Batches of four independent (ldmatrix, mma) pairs: every load of a batch is issued before
         // its first mma, and the four mma of a batch feed four different accumulators, so the
@@ -700,7 +714,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
         if (!a.defer) {  // A/B knob (TTS_MEGA_NODEFER=1): hand the slots back at once
           __syncwarp();
           if (lane == 0)
-            for (int j = 0; j < rel_n; ++j) mbar_arrive(&empty[int((rel_it + j) % STAGES)]);
+            for (int j = 0; j < rel_n; ++j) mbar_arrive(&empty[(rel_it + j) & (STAGES - 1)]);
           rel_n = 0;
         }
         // hi + lo planes: columns c and c + 4 sit two lanes apart
