@@ -141,10 +141,11 @@ def test_fp16_weight_mode_tracks_oracle(pkg, golden, voice, model_dir):
         eng.close()
 
 
-@pytest.mark.parametrize("B", [1, 2, 4])
+@pytest.mark.parametrize("B", [1, 2, 4, 6])
 def test_fp16_decode_tensor_core_path_vs_cuda_core_path_and_oracle(pkg, golden, voice, model_dir, B):
     """f16 weights: the tensor-core persistent step (ar_mega3.cuh, split-f16 activations) against the
-    CUDA-core one (ar_mega2.cuh, TTS_MEGA_V2=1) over a teacher-forced run, and against the oracle."""
+    CUDA-core one (ar_mega2.cuh, TTS_MEGA_V2=1) over a teacher-forced run, and against the oracle.
+    B = 6 runs as two launches per step (4 + 2 candidates)."""
     import _pkg
     import tortoise_oracle as O
     sw = _pkg.import_sub("synth_weights")
@@ -156,7 +157,7 @@ def test_fp16_decode_tensor_core_path_vs_cuda_core_path_and_oracle(pkg, golden, 
         if path == "v2":
             os.environ["TTS_MEGA_V2"] = "1"
         try:
-            eng = pkg.Engine(device=0, dtype=pkg.DTYPE_F16, max_batch=4, max_positions=128)
+            eng = pkg.Engine(device=0, dtype=pkg.DTYPE_F16, max_batch=max(B, 4), max_positions=128)
         finally:
             os.environ.pop("TTS_MEGA_V2", None)
         try:

@@ -6,8 +6,8 @@ pkg = _pkg.import_pkg(); sw = _pkg.import_sub("synth_weights")
 md = os.environ.get("TTS_MODEL_DIR", "/tmp/tortoise_b200_models"); sw.generate(md)
 voice = np.fromfile("tests/golden/models/mol.bin", np.float32)
 g = np.load("tests/golden/ar_b1.npz")
-for B in ((1,) if os.environ.get('B_ONLY') else (1, 2, 4)):
-    eng = pkg.Engine(dtype=pkg.DTYPE_F16, max_batch=4, max_positions=404)
+for B in ((1,) if os.environ.get('B_ONLY') else (1, 2, 4, 8, 16)):
+    eng = pkg.Engine(dtype=pkg.DTYPE_F16, max_batch=max(B, 4), max_positions=404)
     eng.load_ar(md + "/ggml-model.bin")
     eng.ar_prefill(g["tokens"], voice, B)
     for i in range(5): eng.ar_step([100]*B, i+2)

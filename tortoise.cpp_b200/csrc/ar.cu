@@ -300,7 +300,7 @@ template <typename WT>
 static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
   ArModel &m = c->ar;
   ArState &s = c->ars;
-  if (m.mega_epoch >= (1u << 24) - 1) {  // tag generations exhausted: start over with clean buffers
+  if (m.mega_epoch >= (1u << 24) - 64) {  // tag generations exhausted: start over with clean buffers
     uint2 *ptrs[5] = {m.ll_h, m.ll_h2, m.ll_qkv, m.ll_m, m.ll_att};
     for (int i = 0; i < 5; ++i) TTS_CUDA_TRY(cudaMemsetAsync(ptrs[i], 0, m.ll_bytes[i], c->stream));
     m.mega_epoch = 0;
@@ -311,8 +311,7 @@ static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
   a.mel_emb = m.mel_emb; a.mel_pos = m.mel_pos; a.tokens = s.d_tokens;
   a.ll_h = m.ll_h; a.ll_h2 = m.ll_h2; a.ll_qkv = m.ll_qkv; a.ll_m = m.ll_m; a.ll_att = m.ll_att;
   a.logits = s.logits; a.kc = s.kc; a.vc = s.vc;
-  a.B = B; a.Bmax = s.Bmax; a.P = s.P; a.n_past = n_past; a.pos_id = pos_id;
-  a.epoch = ++m.mega_epoch;
+  a.Bmax = s.Bmax; a.P = s.P; a.n_past = n_past; a.pos_id = pos_id;
   a.dbg = m.mega_dbg;
   a.dbg_mode = m.mega_dbg_mode;
   {
@@ -332,15 +331,23 @@ static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
     if (ef < 0) { const char *e = getenv("TTS_MEGA_NOEVICT"); ef = (e && e[0] == '0') ? 1 : 0; }  // TTS_MEGA_NOEVICT=0 turns the hint ON; same-box A/B: 541 us with, 527 us without
     a.evict_first = ef;
   }
-  if (sizeof(WT) == 2 && !c->use_mega_v2) {
-    if (B == 1) launch_mega3_bt<1>(c, a);
-    else if (B == 2) launch_mega3_bt<2>(c, a);
-    else launch_mega3_bt<4>(c, a);
-    return;
+  // up to 4 candidates ride on one weight stream; more candidates = one launch per group of 4
+  // (the exchange buffers are reused: tags are unique per launch)
+  for (int b0 = 0; b0 < B; b0 += 4) {
+    const int Bg = std::min(4, B - b0);
+    a.b0 = b0;
+    a.B = Bg;
+    a.epoch = ++m.mega_epoch;
+    if (sizeof(WT) == 2 && !c->use_mega_v2) {
+      if (Bg == 1) launch_mega3_bt<1>(c, a);
+      else if (Bg == 2) launch_mega3_bt<2>(c, a);
+      else launch_mega3_bt<4>(c, a);
+    } else {
+      if (Bg == 1) launch_mega2_bt<WT, 1>(c, a);
+      else if (Bg == 2) launch_mega2_bt<WT, 2>(c, a);
+      else launch_mega2_bt<WT, 4>(c, a);
+    }
   }
-  if (B == 1) launch_mega2_bt<WT, 1>(c, a);
-  else if (B == 2) launch_mega2_bt<WT, 2>(c, a);
-  else launch_mega2_bt<WT, 4>(c, a);
 }
 
 static void ensure_rows(tts_ctx *c, size_t rows) {
@@ -471,7 +478,7 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
   TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
   if (c->use_mega && s.P <= 1024) {
     TTS_CUDA_TRY(cudaMemcpyAsync(s.d_tokens, s.h_tokens, B * 4, cudaMemcpyHostToDevice, c->stream));
-    if (B <= 4 && !c->use_mega_v1) {
+    if (!c->use_mega_v1) {
       if (c->ar.dtype == TTS_DTYPE_F16) launch_mega2_t<__half>(c, B, s.n_past, pos_id);
       else launch_mega2_t<float>(c, B, s.n_past, pos_id);
     } else {

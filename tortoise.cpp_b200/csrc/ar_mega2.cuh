@@ -61,6 +61,7 @@ struct Mega2Args {
   unsigned int epoch;  // unique per launch (1 .. 2^24-1)
   long long *dbg;      // optional clock trace (TTS_MEGA_TRACE=1: CTA 0, cycle stamps; =2: every CTA, 4 globaltimer stamps per phase)
   int dbg_mode;
+  int b0;  // first candidate of this launch (more than 4 candidates = several launches per step, 4 at a time)
   int evict_first;  // 1: weight stream with the L2 evict-first hint (TTS_MEGA_NOEVICT=1 turns it off)
   int keys_per_split;  // attention: keys per (candidate, head) item before splitting (TTS_MEGA_KPS)
   int poll_spin;  // cycles between two polls of a missing tag (TTS_MEGA_SPIN)
@@ -337,8 +338,8 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
     const int b = item / kHeads, head = item % kHeads;
     const int j0 = t * M2_KV_TILE;
     const int rows = min(j0 + M2_KV_TILE, a.n_past) - j0;
-    const __half *K = a.kc + size_t(li) * layer_kv + ((size_t(b) * kHeads + head) * a.P + j0) * kHeadDim;
-    const __half *V = a.vc + size_t(li) * layer_kv + ((size_t(b) * kHeads + head) * a.P + j0) * kHeadDim;
+    const __half *K = a.kc + size_t(li) * layer_kv + ((size_t(a.b0 + b) * kHeads + head) * a.P + j0) * kHeadDim;
+    const __half *V = a.vc + size_t(li) * layer_kv + ((size_t(a.b0 + b) * kHeads + head) * a.P + j0) * kHeadDim;
     for (int u = tid; u < rows * 8; u += M2_CONSUMERS) {
       const int r = u >> 3, c = u & 7;
       cp_async_cg16(kt + r * M2_KV_LD + c * 8, K + size_t(r) * kHeadDim + c * 8);
@@ -511,7 +512,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
           if (b < B) {
-            const int tok = a.tokens[b];
+            const int tok = a.tokens[a.b0 + b];
             const float *e = a.mel_emb + size_t(tok) * kDim, *pe = a.mel_pos + size_t(a.pos_id) * kDim;
             const float2 e0 = *reinterpret_cast<const float2 *>(e + 2 * tid), e1 = *reinterpret_cast<const float2 *>(e + 512 + 2 * tid);
             const float2 p0 = *reinterpret_cast<const float2 *>(pe + 2 * tid), p1 = *reinterpret_cast<const float2 *>(pe + 512 + 2 * tid);
@@ -708,7 +709,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
           const int which = n >> 10, c = n & 1023;
           if (which != 0) {
             __half *cache = (which == 1 ? a.kc : a.vc) + size_t(li) * layer_kv;
-            cache[(size_t(b) * kHeads + (c >> 6)) * size_t(a.P) * kHeadDim + size_t(a.n_past) * kHeadDim + (c & 63)] = hv16;
+            cache[(size_t(a.b0 + b) * kHeads + (c >> 6)) * size_t(a.P) * kHeadDim + size_t(a.n_past) * kHeadDim + (c & 63)] = hv16;
           }
         } else if (kind == 1) {
           const float o = hres[b * kDim + n] + v;
@@ -723,7 +724,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega2_kernel(M
             for (int rr = 0; rr < nrep; ++rr) st_ll_u32(dst + rr * m_rep, *reinterpret_cast<const uint32_t *>(&h2), out_tag);
           }
         } else {
-          a.logits[size_t(b) * N + n] = v;
+          a.logits[size_t(a.b0 + b) * N + n] = v;
         }
       }
     }

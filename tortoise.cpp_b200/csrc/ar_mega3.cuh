@@ -282,8 +282,8 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
     const int b = item / kHeads, head = item % kHeads;
     const int j0 = t * M2_KV_TILE;
     const int rows = min(j0 + M2_KV_TILE, a.n_past) - j0;
-    const __half *K = a.kc + size_t(li) * layer_kv + ((size_t(b) * kHeads + head) * a.P + j0) * kHeadDim;
-    const __half *V = a.vc + size_t(li) * layer_kv + ((size_t(b) * kHeads + head) * a.P + j0) * kHeadDim;
+    const __half *K = a.kc + size_t(li) * layer_kv + ((size_t(a.b0 + b) * kHeads + head) * a.P + j0) * kHeadDim;
+    const __half *V = a.vc + size_t(li) * layer_kv + ((size_t(a.b0 + b) * kHeads + head) * a.P + j0) * kHeadDim;
     for (int u = tid; u < rows * 8; u += M2_CONSUMERS) {
       const int r = u >> 3, c = u & 7;
       cp_async_cg16(kt + r * M2_KV_LD + c * 8, K + size_t(r) * kHeadDim + c * 8);
@@ -460,7 +460,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
           if (b < B) {
-            const int tok = a.tokens[b];
+            const int tok = a.tokens[a.b0 + b];
             const float *e = a.mel_emb + size_t(tok) * kDim, *pe = a.mel_pos + size_t(a.pos_id) * kDim;
             const float2 e0 = *reinterpret_cast<const float2 *>(e + 2 * tid), e1 = *reinterpret_cast<const float2 *>(e + 512 + 2 * tid);
             const float2 p0 = *reinterpret_cast<const float2 *>(pe + 2 * tid), p1 = *reinterpret_cast<const float2 *>(pe + 512 + 2 * tid);
@@ -756,7 +756,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
             const int which = n >> 10, c = n & 1023;
             if (which != 0) {
               __half *cache = (which == 1 ? a.kc : a.vc) + size_t(li) * layer_kv;
-              cache[(size_t(b) * kHeads + (c >> 6)) * size_t(a.P) * kHeadDim + size_t(a.n_past) * kHeadDim + (c & 63)] = hv16;
+              cache[(size_t(a.b0 + b) * kHeads + (c >> 6)) * size_t(a.P) * kHeadDim + size_t(a.n_past) * kHeadDim + (c & 63)] = hv16;
             }
           } else if (kind == 1) {
             const float o = hres[b * kDim + n] + v;
@@ -769,7 +769,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega3_kernel(M
               for (int rr = 0; rr < nrep; ++rr) st_ll_u32(dst + rr * m_rep, *reinterpret_cast<const uint32_t *>(&h2), out_tag);
             }
           } else {
-            a.logits[size_t(b) * N + n] = v;
+            a.logits[size_t(a.b0 + b) * N + n] = v;
           }
         }
         if (s0 + M3_GROUP < n_stages) bar_consumers();  // the next group overwrites the partial tiles
