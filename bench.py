@@ -50,8 +50,8 @@ HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one decode-step launch, from the committed
 # `ncu --set full` capture (profiles/); per launch like `achieved`
-NCU_TRAFFIC_BYTES = 776120064 + 5641216
-NCU_TRAFFIC_SOURCE = "profiles/r01d_mega3_ncu_full_raw.csv (ar_decode_mega3_kernel<1>, ~20 cached positions)"
+NCU_TRAFFIC_BYTES = 776100096 + 5197056
+NCU_TRAFFIC_SOURCE = "profiles/r01e_mega3_ncu_full_raw.csv (ar_decode_mega3_kernel<1>, ~20 cached positions, 426.6 us under ncu)"
 
 
 def measured_peaks():

@@ -225,70 +225,55 @@ static __global__ void __launch_bounds__(T6_THREADS, T6_MIN_CTAS)
     const bool resid = g.epi == E_BIAS_RESID || g.epi == E_BIAS_LRELU_RESID;
     const uint32_t red_u32 = smem_u32(red);
     double gs1 = 0.0, gs2 = 0.0;
-    // Two rows per warp and pass, every load of the pass in flight before the first use (2 x csz
-    // distributed-shared-memory reads + 2 residual reads): the pass costs one DSMEM round trip
-    // instead of csz dependent ones (the reduction was 3 us of a 9 us kernel, profiles/r01d_tc5v2_timeline.txt).
-    for (int rr0 = warp * 2; rr0 < rows_per; rr0 += 16) {
-      float4 part[2][8], o4[2];
-      bool live[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int r = row_base + rr0 + i;
-        live[i] = rr0 + i < rows_per && r < rows_valid;
-        o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live[i] && vec && resid) o4[i] = *reinterpret_cast<const float4 *>(g.C + size_t(m0 + r) * g.ldc + n);
-      }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int r = row_base + rr0 + i;
-        const uint32_t off = uint32_t(r * T6_RED_LD + c) * 4;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          part[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live[i] && k < csz) {
-            if (csz == 1) part[i][k] = *reinterpret_cast<const float4 *>(red + size_t(r) * T6_RED_LD + c);
-            else part[i][k] = ld_dsmem_f4(red_u32 + off, k);
-          }
+    // (A variant with two rows per warp and all 2 x csz distributed-shared-memory reads of a pass in
+    // flight before the first use measured no faster -- 118.6 vs 112.6 ms for the 80-step stage: the
+    // reduction is bound by DSMEM bandwidth (17-21 B/cycle/SM for the 64 KB a CTA has to read), not
+    // by the latency of dependent loads.)
+    for (int rr = warp; rr < rows_per; rr += 8) {
+      const int r = row_base + rr;
+      if (r >= rows_valid) break;
+      const uint32_t off = uint32_t(r * T6_RED_LD + c) * 4;
+      float4 a4;
+      if (csz == 1) {
+        a4 = *reinterpret_cast<const float4 *>(red + size_t(r) * T6_RED_LD + c);
+      } else {
+        a4 = ld_dsmem_f4(red_u32 + off, 0);
+        for (int k = 1; k < csz; ++k) {
+          const float4 p = ld_dsmem_f4(red_u32 + off, k);
+          a4.x += p.x; a4.y += p.y; a4.z += p.z; a4.w += p.w;
         }
       }
+      const int m = m0 + r;
+      float acc[4] = {a4.x, a4.y, a4.z, a4.w}, out[4];
+      if (vec) {
+        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (resid) o4 = *reinterpret_cast<const float4 *>(g.C + size_t(m) * g.ldc + n);
+        const float old[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        if (!live[i]) continue;
-        const int r = row_base + rr0 + i;
-        float4 a4 = part[i][0];
+        for (int e = 0; e < 4; ++e) out[e] = apply_epi(g.epi, acc[e], bias[e], old[e]);
+        if (g.C) *reinterpret_cast<float4 *>(g.C + size_t(m) * g.ldc + n) = make_float4(out[0], out[1], out[2], out[3]);
+        if (g.Chi) {
+          __half hi[4], lo[4];
 #pragma unroll
-        for (int k = 1; k < 8; ++k)
-          if (k < csz) { a4.x += part[i][k].x; a4.y += part[i][k].y; a4.z += part[i][k].z; a4.w += part[i][k].w; }
-        const int m = m0 + r;
-        float acc[4] = {a4.x, a4.y, a4.z, a4.w}, out[4];
-        if (vec) {
-          const float old[4] = {o4[i].x, o4[i].y, o4[i].z, o4[i].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) out[e] = apply_epi(g.epi, acc[e], bias[e], old[e]);
-          if (g.C) *reinterpret_cast<float4 *>(g.C + size_t(m) * g.ldc + n) = make_float4(out[0], out[1], out[2], out[3]);
-          if (g.Chi) {
-            __half hi[4], lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              hi[e] = __float2half_rn(out[e]);
-              lo[e] = __float2half_rn(out[e] - __half2float(hi[e]));
-            }
-            *reinterpret_cast<uint2 *>(g.Chi + size_t(m) * g.ldh + n) = *reinterpret_cast<uint2 *>(hi);
-            if (g.Clo) *reinterpret_cast<uint2 *>(g.Clo + size_t(m) * g.ldh + n) = *reinterpret_cast<uint2 *>(lo);
+          for (int e = 0; e < 4; ++e) {
+            hi[e] = __float2half_rn(out[e]);
+            lo[e] = __float2half_rn(out[e] - __half2float(hi[e]));
           }
-          gs1 += (double(out[0]) + double(out[1])) + (double(out[2]) + double(out[3]));
-          gs2 += (double(out[0]) * out[0] + double(out[1]) * out[1]) + (double(out[2]) * out[2] + double(out[3]) * out[3]);
-        } else {
-          for (int e = 0; e < 4 && n + e < g.N; ++e) {
-            float old = 0.f;
-            if (resid) old = g.C[size_t(m) * g.ldc + n + e];
-            const float o = apply_epi(g.epi, acc[e], bias[e], old);
-            if (g.C) g.C[size_t(m) * g.ldc + n + e] = o;
-            if (g.Chi) {
-              const __half hi = __float2half_rn(o);
-              g.Chi[size_t(m) * g.ldh + n + e] = hi;
-              if (g.Clo) g.Clo[size_t(m) * g.ldh + n + e] = __float2half_rn(o - __half2float(hi));
-            }
+          *reinterpret_cast<uint2 *>(g.Chi + size_t(m) * g.ldh + n) = *reinterpret_cast<uint2 *>(hi);
+          if (g.Clo) *reinterpret_cast<uint2 *>(g.Clo + size_t(m) * g.ldh + n) = *reinterpret_cast<uint2 *>(lo);
+        }
+        gs1 += (double(out[0]) + double(out[1])) + (double(out[2]) + double(out[3]));
+        gs2 += (double(out[0]) * out[0] + double(out[1]) * out[1]) + (double(out[2]) * out[2] + double(out[3]) * out[3]);
+      } else {
+        for (int e = 0; e < 4 && n + e < g.N; ++e) {
+          float old = 0.f;
+          if (resid) old = g.C[size_t(m) * g.ldc + n + e];
+          const float o = apply_epi(g.epi, acc[e], bias[e], old);
+          if (g.C) g.C[size_t(m) * g.ldc + n + e] = o;
+          if (g.Chi) {
+            const __half hi = __float2half_rn(o);
+            g.Chi[size_t(m) * g.ldh + n + e] = hi;
+            if (g.Clo) g.Clo[size_t(m) * g.ldh + n + e] = __float2half_rn(o - __half2float(hi));
           }
         }
       }
