@@ -191,23 +191,28 @@ static __global__ void silu_split_kernel(const float *in, __half *hi, __half *lo
 // QKV [nseq][T][3072] f32 with head h owning channels [192h, 192h+192): q | k | v.
 // bucket(i, j) = (j > i ? 16 : 0) + rpb[|j - i|] (main.cpp:4722-4749, table from the host).
 // Output as split-f16 planes [nseq*T][1024] (operand of the F32 proj_out matmul).
-// grid (ceil(T/16), 16, nseq) x 128: 4 warps x 4 queries, keys staged in tiles of 64.
-static __global__ void __launch_bounds__(128) diff_attn_kernel(const float *QKV, const float *relbias, const int *rpb,
-                                                        __half *out_hi, __half *out_lo, int T) {
-  constexpr int TK = 64, LDK = kHeadDim + 4;
-  __shared__ __align__(16) float Ks[TK][LDK];
-  __shared__ __align__(16) float Vs[TK][LDK];
-  __shared__ __align__(16) float Qs[16][kHeadDim];
-  __shared__ float Ps[4][4][TK];
-  __shared__ float bias_s[32];
+// grid (ceil(T / DA_Q), 16, nseq) x DA_THREADS: 8 warps x 4 queries, keys staged in tiles of 64.
+// (32 queries per block instead of 16: every block re-reads the K and V of its head from L2 --
+// 98 KB at T = 191 -- so the block count per head IS the L2 traffic: 37.6 -> 18.8 MB per call.)
+constexpr int DA_WARPS = 8, DA_THREADS = DA_WARPS * 32, DA_Q = DA_WARPS * 4, DA_TK = 64, DA_LDK = kHeadDim + 4;
+constexpr size_t DA_SMEM = (size_t(2) * DA_TK * DA_LDK + size_t(DA_Q) * kHeadDim + size_t(DA_WARPS) * 4 * DA_TK + 32) * sizeof(float);
+static __global__ void __launch_bounds__(DA_THREADS) diff_attn_kernel(const float *QKV, const float *relbias, const int *rpb,
+                                                               __half *out_hi, __half *out_lo, int T) {
+  constexpr int TK = DA_TK, LDK = DA_LDK;
+  extern __shared__ __align__(16) float da_smem[];
+  float (*Ks)[LDK] = reinterpret_cast<float (*)[LDK]>(da_smem);
+  float (*Vs)[LDK] = reinterpret_cast<float (*)[LDK]>(da_smem + TK * LDK);
+  float (*Qs)[kHeadDim] = reinterpret_cast<float (*)[kHeadDim]>(da_smem + 2 * TK * LDK);
+  float (*Ps)[4][TK] = reinterpret_cast<float (*)[4][TK]>(da_smem + 2 * TK * LDK + DA_Q * kHeadDim);
+  float *bias_s = da_smem + 2 * TK * LDK + DA_Q * kHeadDim + DA_WARPS * 4 * TK;
   pdl_launch_dependents();
   pdl_wait();
   const int t = threadIdx.x, warp = t / 32, lane = t % 32;
   const int head = blockIdx.y, seq = blockIdx.z;
-  const int q0 = blockIdx.x * 16;
+  const int q0 = blockIdx.x * DA_Q;
   const float *base = QKV + size_t(seq) * T * 3072 + head * 192;
   if (t < 32) bias_s[t] = 8.0f * relbias[t * 16 + head];
-  for (int i = t; i < 16 * kHeadDim; i += 128) {
+  for (int i = t; i < DA_Q * kHeadDim; i += DA_THREADS) {
     const int r = i / kHeadDim, d = i % kHeadDim;
     const int qi = q0 + r;
     Qs[r][d] = qi < T ? base[size_t(qi) * 3072 + d] : 0.f;
@@ -221,7 +226,7 @@ static __global__ void __launch_bounds__(128) diff_attn_kernel(const float *QKV,
   }
   for (int k0 = 0; k0 < T; k0 += TK) {
     __syncthreads();
-    for (int i = t; i < TK * (kHeadDim / 4); i += 128) {
+    for (int i = t; i < TK * (kHeadDim / 4); i += DA_THREADS) {
       const int r = i / (kHeadDim / 4), c = (i % (kHeadDim / 4)) * 4;
       const int kj = k0 + r;
       float4 kv = make_float4(0, 0, 0, 0), vv = kv;

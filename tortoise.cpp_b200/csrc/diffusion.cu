@@ -274,7 +274,12 @@ static void attn_block(tts_ctx *c, const Launcher &L, const DAttn &a, float *x, 
   DiffModel &m = *c->diff;
   gn(c, L, x, a.n_w, a.n_b, nullptr, m.A16, nullptr, nseq, T, 0);
   conv(c, L, m.A16, a.w_qkv, a.b_qkv, m.QKV, nseq, T, kDim, 3072, 1, 3072, E_BIAS);
-  L(diff_attn_kernel, dim3((T + 15) / 16, kHeads, nseq), dim3(128), 0, (const float *)m.QKV,
+  static bool da_attr = false;
+  if (!da_attr) {
+    TTS_CUDA_TRY(cudaFuncSetAttribute(diff_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DA_SMEM)));
+    da_attr = true;
+  }
+  L(diff_attn_kernel, dim3((T + DA_Q - 1) / DA_Q, kHeads, nseq), dim3(DA_THREADS), DA_SMEM, (const float *)m.QKV,
     (const float *)a.relbias, (const int *)m.rpb, m.ATThi, m.ATTlo, T);
   tg(c, L, m.ATThi, m.ATTlo, a.proj_hi, a.proj_lo, a.b_proj, x, nseq * T, kDim, kDim, kDim, kDim, E_BIAS_RESID,
      1, T, 0);  // per-sequence M tiles so the fused GroupNorm statistics stay per sequence
