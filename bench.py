@@ -38,10 +38,19 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-PROMPT = "this is a test message."
+# TTS_BENCH_CONFIG=C3 switches to BASELINE.json configs[2] (16 candidates batched on one GPU, 50-char prompt,
+# best-candidate select); the default is configs[1] (the config the metric is quoted on).
+CONFIG = os.environ.get("TTS_BENCH_CONFIG", "C2").upper()
+if CONFIG == "C3":
+    PROMPT = "the quick brown fox jumps over the lazy dog again."
+    CANDIDATES = 16
+else:
+    PROMPT = "this is a test message."
+    CANDIDATES = 1
+assert CONFIG != "C3" or len(PROMPT) == 50
 # profiling-only knobs (ncu replays every launch ~40x; a full 58k-launch step is not profilable):
 # the same code path with fewer repetitions.  Non-default values are flagged in `config`.
-N_CODES = int(os.environ.get("TTS_BENCH_CODES", "35"))          # round(1.5 * len(PROMPT)) = 34.5 -> 35
+N_CODES = int(os.environ.get("TTS_BENCH_CODES", "75" if CONFIG == "C3" else "35"))  # round(1.5 * len(PROMPT))
 DIFF_STEPS = int(os.environ.get("TTS_BENCH_DIFF_STEPS", "80"))
 MODEL_DIR = os.environ.get("TTS_MODEL_DIR", "/tmp/tortoise_b200_models")
 GOLDEN_MODELS = os.path.join(ROOT, "tests", "golden", "models")
@@ -202,13 +211,15 @@ def stage_hbm(sm_ar_ms, diff_ms, voc_ms, n_dec, step_bytes, peak):
 
 
 def workload_config(world):
-    return {"workload": "configs[1]: 1 candidate/GPU, prompt 'this is a test message.' (T=16), voice mol.bin, "
-                        f"{N_CODES} mel codes forced, {DIFF_STEPS} diffusion steps, full AR+diffusion+vocoder",
-            "candidates_per_gpu": 1, "global_candidates": world, "prompt_chars": len(PROMPT),
+    name = ("configs[2]: 16 candidates batched per GPU, best-candidate select, 50-char prompt" if CONFIG == "C3"
+            else "configs[1]: 1 candidate/GPU, prompt 'this is a test message.' (T=16)")
+    return {"workload": f"{name}, voice mol.bin, {N_CODES} mel codes forced, {DIFF_STEPS} diffusion steps, "
+                        "full AR+diffusion+vocoder",
+            "candidates_per_gpu": CANDIDATES, "global_candidates": world * CANDIDATES, "prompt_chars": len(PROMPT),
             "diffusion_steps": DIFF_STEPS, "weights": "seeded synthetic (tortoise.cpp_b200/synth_weights.py)",
             "l2_policy": "inputs larger than L2: 0.77 GB of f16 AR weights + 0.36 GB of diffusion weights are "
                          "re-streamed every step (L2 = 126 MB)",
-            "reduced_for_profiling": (N_CODES != 35 or DIFF_STEPS != 80),
+            "reduced_for_profiling": (N_CODES != (75 if CONFIG == "C3" else 35) or DIFF_STEPS != 80),
             "parallelism": f"dp{world} (candidates sharded, weights replicated)"}
 
 
@@ -246,7 +257,8 @@ def main():
     hostmod = _pkg.import_sub("host")
     distmod = _pkg.import_sub("dist")
     hl = hostmod.HostLib(full=True)
-    eng = pkg.Engine(device=local_rank, dtype=pkg.DTYPE_F16, max_batch=2, max_positions=404, parity_quirks=True)
+    eng = pkg.Engine(device=local_rank, dtype=pkg.DTYPE_F16, max_batch=max(2, CANDIDATES), max_positions=404,
+                     parity_quirks=True)
     eng.load_ar(os.path.join(MODEL_DIR, "ggml-model.bin"))
     eng.load_diffusion(os.path.join(MODEL_DIR, "ggml-diffusion-model.bin"))
     eng.load_vocoder(os.path.join(MODEL_DIR, "ggml-vocoder-model.bin"))
@@ -261,19 +273,21 @@ def main():
         # AR through the stage driver; device time = sum of the per-call CUDA-event times is not
         # observable from outside the driver, so time the three stage calls individually below.
         t0 = time.perf_counter()
-        codes, lat, nlat, score, steps = hl.autoregressive(eng, rng, tokens, voice, 1, forced_codes=N_CODES,
+        B = CANDIDATES
+        codes, lat, nlat, score, steps = hl.autoregressive(eng, rng, tokens, voice, B, forced_codes=N_CODES,
                                                            per_candidate_stop=True)
         t_ar = time.perf_counter() - t0
-        L = int(nlat[0])
-        mel = hl.diffusion(eng, rng, lat[0, :L], DIFF_STEPS)
+        win = int(np.argmax(score))  # best-candidate select (the reference has no scorer and takes candidate 0)
+        L = int(nlat[win])
+        mel = hl.diffusion(eng, rng, lat[win, :L], DIFF_STEPS)
         d_ms = eng.last_stage_ms
         audio = hl.vocoder(eng, rng, mel)
         v_ms = eng.last_stage_ms
         S = mel.shape[1]
-        h2d = 4 * (T + 1024) + steps * 4 + 4 * (T + 1024 + 502) + 4 * L * 1024 + 4 * (DIFF_STEPS + 1) * 100 * S \
+        h2d = 4 * (T + 1024) + steps * 4 * B + 4 * (T + 1024 + 502 * B) + 4 * L * 1024 + 4 * (DIFF_STEPS + 1) * 100 * S \
             + 4 * 100 * S + 4 * (S + 10) * 64
-        d2h = 4 * 8194 * steps + 4 * 500 * 1024 + 4 * 100 * S + 4 * audio.size
-        return audio, t_ar, d_ms, v_ms, steps, float(score[0]), h2d, d2h
+        d2h = 4 * 8194 * steps * B + 4 * 500 * 1024 * B + 4 * 100 * S + 4 * audio.size
+        return audio, t_ar, d_ms, v_ms, steps * B, float(score[win]), h2d, d2h
 
     for w in range(args.warmup):
         one_utterance(1000 + w)
@@ -302,7 +316,8 @@ def main():
         h2d, d2h = bi, bo
         last_score = score
         if world > 1:  # final candidate gather / selection (the path's only exchange; NCCL)
-            winner, owner, _, _ = distmod.gather_select([score], [steps], device=torch.device("cuda", local_rank))
+            winner, owner, _, _ = distmod.gather_select([score], [steps // CANDIDATES],
+                                                        device=torch.device("cuda", local_rank))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -330,6 +345,12 @@ def main():
     eng.ar_prefill(tokens, voice, 1)
     step_ms, step_bytes = eng.bench_decode_step(200)
     achieved = step_bytes / step_ms / 1e6
+    batched = None
+    if CANDIDATES > 1:  # the same measurement with all candidates of the config riding on the weight stream(s)
+        eng.ar_prefill(tokens, voice, CANDIDATES)
+        b_ms, b_bytes = eng.bench_decode_step(100)
+        batched = {"candidates": CANDIDATES, "us_per_step": b_ms * 1e3, "tok_s": CANDIDATES / (b_ms * 1e-3),
+                   "GBs": b_bytes / b_ms / 1e6, "launches_per_step": (CANDIDATES + 3) // 4}
     per_op = {}
     for op, name in enumerate(["qkv", "attn_proj", "fc", "mlp_proj"]):  # per-op streaming GEMV (fallback path)
         ms, by = eng.bench_gemv(op, 1, 240)
@@ -345,7 +366,7 @@ def main():
         # achieved fraction of the HBM roofline per stage (north star): algorithmic weight bytes of the stage
         # (each decode step / sampling step / vocoder pass streams its weights once) over device time
         "stage_hbm": stage_hbm(sm_ar_ms=ar_dev_ms, diff_ms=diff_ms / args.steps, voc_ms=voc_ms / args.steps,
-                               n_dec=n_tokens / args.steps, step_bytes=step_bytes, peak=peak),
+                               n_dec=n_tokens / args.steps / CANDIDATES, step_bytes=step_bytes, peak=peak),
         "e2e": {"value": audio_total / wall, "unit": "audio-s/wall-s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
@@ -356,7 +377,7 @@ def main():
                                "(30 layers x 4 GEMV phases + attention + lm_head, persistent, 148 CTAs); bytes = "
                                "386.29 M weights x 2 B + KV + embeddings + logits",
                      "us_per_launch": step_ms * 1e3, "bytes_per_launch": step_bytes,
-                     "per_op_wsgemv_kernel": per_op},
+                     "per_op_wsgemv_kernel": per_op, "decode_step_batched": batched},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
