@@ -34,6 +34,15 @@ void tts_rng_normal(tts_rng *r, float *out, int64_t n); /* sample_normal_noise (
 int tts_host_tokenize(const char *tokenizer_json_path, const char *message, int32_t *out, int cap);
 int tts_host_vocab_size(const char *tokenizer_json_path);
 
+/* ---- optional text front-end (not in the reference, which accepts only [a-z .,!?'-],
+ *      README.md:32; OFF by default, the CLI turns it on with --normalize).
+ *      normalize: lower-case, numbers and & % + = @ $ spelled out, other characters -> space.
+ *      Returns the length written (NUL-terminated) or -(bytes needed) when cap is too small.
+ *      split: sentence-boundary chunks of at most max_chars characters; writes (start, end)
+ *      byte offsets into spans_out[2 * cap_spans], returns the chunk count (or <0). ------- */
+int tts_host_normalize_text(const char *in, char *out, int cap);
+int tts_host_split_text(const char *in, int max_chars, int32_t *spans_out, int cap_spans);
+
 /* ---- process_logits_and_sample (main.cpp:4753-4806): repetition penalty 2.0 over the
  *      previous inputs prev[B][n_prev], temperature 0.8, top-k 50, top-p (cum <= 0.2 cut),
  *      softmax, multinomial (two uniforms per candidate, second used).  logits [B][8194] is

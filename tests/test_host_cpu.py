@@ -137,3 +137,34 @@ def test_no_gpu_means_loud_failure_not_fallback():
     with pytest.raises(pkg.TTSError) as e:
         pkg.Engine()
     assert e.value.code == -3  # TTS_ENODEV
+
+
+def test_text_front_end_normalize_and_split(hl):
+    """optional front-end (SURVEY 8f #3): everything it emits is in the reference's alphabet."""
+    n = hl.normalize_text
+    assert n("this is a test message.") == "this is a test message."          # supported text is untouched
+    assert n("Hello, World!") == "hello, world!"
+    assert n("I have 2 cats & 21 dogs") == "i have two cats and twenty-one dogs"
+    assert n("It costs $1500.") == "it costs one thousand five hundred dollars."
+    assert n("pi is 3.14") == "pi is three point one four"
+    assert n("100% sure") == "one hundred percent sure"
+    assert n("1000000 and 1000001") == "one million and one million one"
+    assert n("x=y+z @ home") == "x equals y plus z at home"
+    assert n("café — naïve") == "caf na ve"                      # non-ASCII bytes -> space
+    assert n("  a   b  ,c ") == "a b,c"
+    assert n("12345678901234567") == " ".join(
+        ["one", "two", "three", "four", "five", "six", "seven", "eight", "nine", "zero", "one", "two", "three", "four",
+         "five", "six", "seven"])
+    import re
+    for s in ("Dr. Freeman? 42!", "A+B=C", "tel: 555-0199", "\t\ttabs\nnewlines"):
+        assert re.fullmatch(r"[a-z .,!?'-]*", n(s)), n(s)
+    text = ("this is the first sentence. here is a second one, with a comma! and a third? "
+            "finally a very long tail without any punctuation that has to be cut at a space somewhere")
+    for limit in (20, 40, 80, 1000):
+        parts = hl.split_text(text, limit)
+        assert all(0 < len(p) <= limit for p in parts)
+        assert " ".join(parts).split() == text.split()                          # nothing lost, order kept
+    assert hl.split_text(text, 40)[0] == "this is the first sentence."
+    assert hl.split_text("short", 100) == ["short"]
+    assert hl.split_text("", 100) == []
+    assert hl.split_text("a" * 50, 16) == ["a" * 16, "a" * 16, "a" * 16, "aa"]

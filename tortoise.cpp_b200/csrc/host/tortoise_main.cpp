@@ -2,7 +2,8 @@
 // model paths and output format as the reference CLI (main.cpp:6528-6584).  Flags are parsed
 // pairwise left to right and the last argv element is never treated as a flag (`i < argc-1`).
 // Extra, non-reference flags (all default to reference behaviour): --candidates N,
-// --steps N, --dtype f32|f16, --models DIR, --device N, --bench-json.
+// --steps N, --dtype f32|f16, --models DIR, --device N, --bench-json, --normalize (spell out
+// numbers / symbols and lower-case the message before tokenisation).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -38,8 +39,15 @@ int main(int argc, char **argv) {
     else if (a == "--models") models = argv[i + 1];
     else if (a == "--device") device = std::stoi(argv[i + 1]);
   }
-  for (int i = 1; i < argc; ++i)
+  bool normalize = false;
+  for (int i = 1; i < argc; ++i) {
     if (std::string(argv[i]) == "--bench-json") bench_json = true;
+    if (std::string(argv[i]) == "--normalize") normalize = true;
+  }
+  if (normalize) {
+    std::vector<char> buf(16 * message.size() + 64);
+    if (tts_host_normalize_text(message.c_str(), buf.data(), int(buf.size())) >= 0) message = buf.data();
+  }
   if (!seeded) {  // wall-clock milliseconds, like the reference's global initialiser (main.cpp:39-47)
     seed = unsigned(std::chrono::duration_cast<std::chrono::milliseconds>(
                         std::chrono::system_clock::now().time_since_epoch()).count());

@@ -37,6 +37,8 @@ class HostLib:
         lib.tts_rng_normal.argtypes = [vp, f32p, C.c_int64]
         lib.tts_host_tokenize.argtypes = [C.c_char_p, C.c_char_p, i32p, i32]
         lib.tts_host_vocab_size.argtypes = [C.c_char_p]
+        lib.tts_host_normalize_text.argtypes = [C.c_char_p, C.c_char_p, i32]
+        lib.tts_host_split_text.argtypes = [C.c_char_p, i32, i32p, i32]
         lib.tts_host_sample.argtypes = [vp, f32p, i32p, i32, i32, i32p, f32p]
         lib.tts_host_sample_reference_order.argtypes = [vp, f32p, i32p, i32, i32, i32p]
         lib.tts_host_apply_padding.argtypes = [i32p, i32, i32p]
@@ -65,6 +67,21 @@ class HostLib:
         if n < 0:
             raise RuntimeError(f"tokenize failed: {n}")
         return list(out[:n])
+
+    def normalize_text(self, text: str) -> str:
+        buf = C.create_string_buffer(16 * len(text.encode()) + 64)
+        n = self.lib.tts_host_normalize_text(text.encode(), buf, len(buf))
+        if n < 0:
+            raise RuntimeError(f"normalize_text failed: {n}")
+        return buf.value.decode()
+
+    def split_text(self, text: str, max_chars: int) -> list[str]:
+        raw = text.encode()
+        spans = (C.c_int32 * (2 * (len(raw) + 1)))()
+        n = self.lib.tts_host_split_text(raw, max_chars, spans, len(raw) + 1)
+        if n < 0:
+            raise RuntimeError(f"split_text failed: {n}")
+        return [raw[spans[2 * i]:spans[2 * i + 1]].decode() for i in range(n)]
 
     def vocab_size(self, tokenizer_json: str) -> int:
         return self.lib.tts_host_vocab_size(os.fsencode(tokenizer_json))
