@@ -60,6 +60,35 @@ def test_sampler_fast_equals_literal_on_random_logits(hl):
         assert np.array_equal(a, b)
 
 
+def test_sampler_fast_path_threshold_edge_cases(hl):
+    """the heap-based top-k threshold of the fast path against the literal algorithm where it could go
+    wrong: values one ulp around the 50th largest, quotients that collide after the division by the
+    temperature, many equal values at the threshold, penalised entries at the threshold, negatives."""
+    rs = np.random.RandomState(7)
+    cases = []
+    for trial in range(40):
+        lg = (rs.randn(2, 8194) * rs.choice([0.01, 1.0, 20.0])).astype(np.float32)
+        if trial % 4 == 1:  # a ladder of adjacent floats straddling the 50th largest value
+            top = np.sort(lg[0])[-50]
+            ladder = top
+            for k in range(12):
+                lg[0, 1000 + k] = ladder
+                ladder = np.nextafter(ladder, np.float32(-np.inf), dtype=np.float32)
+        if trial % 4 == 2:  # a plateau of equal values exactly at the threshold (ties -> literal path)
+            lg[1, 300:340] = np.sort(lg[1])[-50]
+        if trial % 4 == 3:  # all negative, tiny spread
+            lg = -np.abs(lg) - np.float32(5.0)
+        prev = rs.randint(0, 8194, size=(2, 6)).astype(np.int32)
+        if trial % 5 == 0:  # penalised entries among the largest
+            prev[0, :3] = np.argsort(lg[0])[-3:]
+        cases.append((lg, prev))
+    for i, (lg, prev) in enumerate(cases):
+        for seed in (0, 1):
+            a = hl.sample(hl.rng(seed), lg, prev)
+            b = hl.sample(hl.rng(seed), lg, prev, literal=True)
+            assert np.array_equal(a, b), i
+
+
 def test_padding_and_trim(hl):
     import tortoise_oracle as O
     g = np.load(os.path.join(GOLDEN, "hostfn.npz"))

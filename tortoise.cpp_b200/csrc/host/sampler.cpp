@@ -9,6 +9,7 @@
 //    survivors in the same order.  If two survivors tie (the only case where std::sort's
 //    unspecified order of equal keys could matter) it defers to sample_literal().
 #include <algorithm>
+#include <functional>
 #include <cassert>
 #include <cmath>
 #include <cstdint>
@@ -78,18 +79,52 @@ int sample_literal_one(Rng &r, const float *logits_row, const int32_t *prev, int
   return multinomial(r, lg.data(), V);
 }
 
+// 50th largest value of x[0..V) = root of a min-heap of the 50 largest seen so far: one pass in
+// which almost every element fails a single (well-predicted) comparison.  (An AVX2 variant testing
+// 8 elements per instruction measured no faster than this loop -- ~10 us per row either way.)
+static float kth_largest_50(const float *x) {
+  float heap[50];
+  for (int i = 0; i < 50; ++i) heap[i] = x[i];
+  std::make_heap(heap, heap + 50, std::greater<float>());
+  for (int i = 50; i < V; ++i) {
+    const float v = x[i];
+    if (v > heap[0]) {
+      std::pop_heap(heap, heap + 50, std::greater<float>());
+      heap[49] = v;
+      std::push_heap(heap, heap + 50, std::greater<float>());
+    }
+  }
+  return heap[0];
+}
+
 // returns -1 when it must defer to the literal path (ties among survivors)
+//
+// Cost matters: the sampler sits between two decode steps (a step is ~0.45 ms on B200, and 16
+// candidates are sampled one after the other).  The 50th-largest value is found with a 50-entry
+// min-heap in ONE pass over the penalised raw logits (division by the temperature is monotone,
+// so it is applied to the handful of candidates around the threshold only; the survivor test
+// itself is done on the divided values exactly as the reference does it).
 static int sample_fast_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev, float *logprob) {
-  std::vector<float> lg(logits_row, logits_row + V);
+  thread_local std::vector<float> lg;
+  lg.assign(logits_row, logits_row + V);
   penalise(lg, prev, n_prev);
   const float temp = 0.8;
-  for (float &x : lg) x /= temp;
-  std::vector<float> s(lg);
-  std::nth_element(s.begin(), s.begin() + (V - 50), s.end());
-  const float kth = s[V - 50];
-  std::vector<std::pair<float, int>> surv;  // (value, index), in index order
-  for (int i = 0; i < V; ++i)
-    if (!(lg[i] < kth)) surv.push_back(std::make_pair(lg[i], i));
+  const float kth_raw = kth_largest_50(lg.data());
+  const float kth = kth_raw / temp;  // == s[V - 50] of the divided array (x -> x / temp is monotone)
+  // survivors: !(x / temp < kth).  x >= kth_raw always survives; below it only values whose
+  // quotient rounds up to kth can -- they are within a few ulp of kth_raw.
+  const float slack = std::fabs(kth_raw) * 4e-7f + 1e-37f;
+  const float lo = kth_raw - slack;
+  std::vector<std::pair<float, int>> surv;  // (value / temp, index), in index order
+  surv.reserve(64);
+  auto consider = [&](int i) {
+    const float x = lg[i];
+    if (x >= lo) {
+      const float q = x / temp;
+      if (!(q < kth)) surv.push_back(std::make_pair(q, i));
+    }
+  };
+  for (int i = 0; i < V; ++i) consider(i);
   std::vector<std::pair<float, int>> asc(surv);
   std::sort(asc.begin(), asc.end());  // by value, then index
   for (size_t i = 1; i < asc.size(); ++i)
@@ -104,18 +139,18 @@ static int sample_fast_one(Rng &r, const float *logits_row, const int32_t *prev,
     e[i] = std::exp(asc[i].first);
     sum += e[i];
   }
-  std::vector<char> dead(V, 0);
+  std::vector<int> dead;  // indices cut by top-p (a handful)
   float cum = 0;
   for (int i = 0; i < ns; ++i) {
     const float p = e[i] / sum;
     cum = (i == 0) ? p : cum + p;  // masked prefix sums to exactly 0.0f
-    if (i < ns - 1 && cum <= 0.2) dead[asc[i].second] = 1;  // the last (largest) entry is never cut
+    if (i < ns - 1 && cum <= 0.2) dead.push_back(asc[i].second);  // the last (largest) entry is never cut
   }
   // final softmax + multinomial in index order over what is left
   std::vector<std::pair<float, int>> fin;
   float fsum = 0;
   for (const auto &pr : surv)
-    if (!dead[pr.second]) {
+    if (std::find(dead.begin(), dead.end(), pr.second) == dead.end()) {
       const float ex = std::exp(pr.first);
       fin.push_back(std::make_pair(ex, pr.second));
       fsum += ex;
@@ -152,10 +187,9 @@ static int sample_fast_one(Rng &r, const float *logits_row, const int32_t *prev,
 }
 
 int sample_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev, float *logprob) {
-  const Rng saved = r;
+  // (the fast path draws from the generator only after it has decided not to defer)
   const int s = sample_fast_one(r, logits_row, prev, n_prev, logprob);
   if (s >= 0) return s;
-  r = saved;  // fast path consumed nothing before deciding, but stay safe
   if (logprob) *logprob = 0.f;
   return sample_literal_one(r, logits_row, prev, n_prev);
 }
