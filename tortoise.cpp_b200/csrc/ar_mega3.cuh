@@ -1,5 +1,5 @@
 // ar_mega3.cuh -- AR decode step as one persistent kernel, third generation (f16 weights):
-// the GEMV of every phase runs on the tensor cores.
+// the K = 1024 GEMV phases run on the tensor cores (the K = 4096 phase too for 4 candidates).
 //
 // Same math and the same cross-CTA protocol as ar_mega2.cuh (reference graph
 // autoregressive_graph(fake_inputs=false), main.cpp:2668-3029).  What changed, and why
@@ -19,7 +19,12 @@
 //   * each warp owns K/8 of the reduction for ALL rows of the phase (8 or 32 k-steps), waits once
 //     for the phase's stages, and the eight partial tiles are summed through shared memory in a
 //     fixed order (deterministic).
-// Instruction count per phase drops ~10x; 1, 2 or 4 candidates cost the same.
+// 1, 2 or 4 candidates cost the same in these phases.  Measured afterwards (clock trace,
+// profiles/r01_decode_step.md): HMMA.16816 issues only every ~30-48 cycles per scheduler on B200,
+// so the K = 4096 phase (32 MMAs per warp for 6-8 useful rows) stays on the CUDA cores for 1-2
+// candidates; the other changes of this generation (deferred ring-slot release, one attention
+// item per head over 128-key tiles, same-round re-polling, 32-bit ring counters) are described
+// where they are implemented.
 #pragma once
 #include "ar_mega2.cuh"
 
