@@ -126,22 +126,6 @@ int64_t tts_launch_count(const tts_ctx *ctx);
 float tts_last_stage_ms(const tts_ctx *ctx);
 /* sum of the device-side durations of all stage calls since tts_init (CUDA events) */
 double tts_device_ms_total(const tts_ctx *ctx);
-/* micro-benchmark of the streaming GEMV kernel over all 30 layers' weights (what
- * bench.py's roofline figure is computed from): returns average ms per launch and the
- * algorithmic bytes per launch for the chosen op (0 qkv,1 attn-proj,2 fc,3 mlp-proj,4 lm-head) */
-int tts_bench_gemv(tts_ctx *ctx, int32_t op, int32_t B, int32_t iters, float *ms_per_launch,
-                   double *bytes_per_launch);
-
-/* `iters` consecutive decode steps (after tts_ar_prefill) timed with CUDA events on the stream,
- * no host round trip in between: average ms per step and the algorithmic bytes of one step
- * (streamed weights + KV read/append + embeddings + logits). */
-int tts_bench_decode_step(tts_ctx *ctx, int32_t iters, float *ms_per_step, double *bytes_per_step);
-
-/* micro-benchmark of the streaming mechanism (148 CTAs, disjoint contiguous HBM slices):
- * mode 0 = ring of TMA bulk copies (stage_bytes x stages), mode 1 = plain LDG.128 loads. */
-int tts_bench_stream(tts_ctx *ctx, int32_t mode, int32_t stage_bytes, int32_t stages, int64_t bytes_per_cta,
-                     int32_t iters, float *ms_per_launch, double *bytes_per_launch);
-
 #ifdef __cplusplus
 }
 #endif

@@ -82,7 +82,6 @@ def load_library() -> C.CDLL:
     lib.tts_device_ms_total.argtypes = [vp]
     lib.tts_device_ms_total.restype = C.c_double
     lib.tts_bench_decode_step.argtypes = [vp, i32, P(C.c_float), P(C.c_double)]
-    lib.tts_bench_stream.argtypes = [vp, i32, i32, i32, C.c_int64, i32, P(C.c_float), P(C.c_double)]
     lib.tts_bench_gemv.argtypes = [vp, i32, i32, i32, P(C.c_float), P(C.c_double)]
     _lib = lib
     return lib
@@ -217,11 +216,6 @@ class Engine:
     def bench_decode_step(self, iters):
         ms, by = C.c_float(), C.c_double()
         self._chk(self.lib.tts_bench_decode_step(self.h, iters, C.byref(ms), C.byref(by)))
-        return ms.value, by.value
-
-    def bench_stream(self, mode, stage_bytes, stages, bytes_per_cta, iters=10):
-        ms, by = C.c_float(), C.c_double()
-        self._chk(self.lib.tts_bench_stream(self.h, mode, stage_bytes, stages, bytes_per_cta, iters, C.byref(ms), C.byref(by)))
         return ms.value, by.value
 
     def bench_gemv(self, op, B, iters):

@@ -8,7 +8,6 @@
 #include "engine.h"
 #include "gemm_launch.cuh"
 #include "wsgemv.cuh"
-#include "ar_mega.cuh"
 #include "ar_mega2.cuh"
 #include "ar_mega3.cuh"
 
@@ -28,7 +27,7 @@ static void *upload_matrix(tts_ctx *c, const Container &ct, const std::string &n
   size_t n = 0;
   read_tensor_to_staging(c, ct, name, &n);
   void *d = nullptr;
-  TTS_CUDA_TRY(cudaMalloc(&d, n * wbytes(c->cfg.dtype)));
+  TTS_CUDA_TRY(ctx_malloc(c, &d, n * wbytes(c->cfg.dtype)));
   if (file_is_kn) {
     dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
     if (c->cfg.dtype == TTS_DTYPE_F16)
@@ -54,8 +53,8 @@ static void make_planes(tts_ctx *c, const void *w, size_t n, __half **hi, __half
     *lo = nullptr;
     return;
   }
-  TTS_CUDA_TRY(cudaMalloc(hi, n * 2));
-  TTS_CUDA_TRY(cudaMalloc(lo, n * 2));
+  TTS_CUDA_TRY(ctx_malloc(c, hi, n * 2));
+  TTS_CUDA_TRY(ctx_malloc(c, lo, n * 2));
   split_f16_kernel<<<1024, 256, 0, c->stream>>>((const float *)w, *hi, *lo, n);
   TTS_CUDA_TRY(cudaGetLastError());
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -66,6 +65,7 @@ void ar_load(tts_ctx *c, const char *path) {
   std::string err;
   if (!ct.open(path, err)) throw ArgError(err, TTS_EIO);
   ArModel &m = c->ar;
+  if (m.loaded) throw ArgError("AR model already loaded in this context");
   m.dtype = c->cfg.dtype;
   m.decode_weight_bytes = 0;
   std::set<std::string> known;
@@ -115,21 +115,21 @@ void ar_load(tts_ctx *c, const char *path) {
   s.Bmax = c->cfg.max_batch;
   s.P = c->cfg.max_positions;
   const size_t B = s.Bmax;
-  TTS_CUDA_TRY(cudaMalloc(&s.h, B * kDim * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.q, B * kDim * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.attn, B * kDim * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.m, B * kFF * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.logits, B * kMelVocab * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.h, B * kDim * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.q, B * kDim * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.attn, B * kDim * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.m, B * kFF * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.logits, B * kMelVocab * 4));
   const size_t kv = size_t(kLayers) * B * kHeads * s.P * kHeadDim;
-  TTS_CUDA_TRY(cudaMalloc(&s.kc, kv * 2));
-  TTS_CUDA_TRY(cudaMalloc(&s.vc, kv * 2));
-  TTS_CUDA_TRY(cudaMalloc(&s.d_tokens, B * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.d_state, 16));
-  TTS_CUDA_TRY(cudaMallocHost(&s.h_tokens, B * 4));
-  TTS_CUDA_TRY(cudaMallocHost(&s.h_state, 16));
-  TTS_CUDA_TRY(cudaMallocHost(&s.h_logits, B * kMelVocab * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.d_text, 1024 * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.d_voice, kDim * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.kc, kv * 2));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.vc, kv * 2));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.d_tokens, B * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.d_state, 16));
+  TTS_CUDA_TRY(ctx_malloc_host(c, &s.h_tokens, B * 4));
+  TTS_CUDA_TRY(ctx_malloc_host(c, &s.h_state, 16));
+  TTS_CUDA_TRY(ctx_malloc_host(c, &s.h_logits, B * kMelVocab * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.d_text, 1024 * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.d_voice, kDim * 4));
   {
     std::vector<MegaLayer> ml(kLayers);
     for (int i = 0; i < kLayers; ++i) {
@@ -137,9 +137,8 @@ void ar_load(tts_ctx *c, const char *path) {
       ml[i] = MegaLayer{l.ln1_w, l.ln1_b, l.ln2_w, l.ln2_b, l.w_qkv, l.w_proj, l.w_fc, l.w_proj2,
                         l.b_qkv,  l.b_proj, l.b_fc,  l.b_proj2};
     }
-    TTS_CUDA_TRY(cudaMalloc(&m.mega_layers, sizeof(MegaLayer) * kLayers));
+    TTS_CUDA_TRY(ctx_malloc(c, &m.mega_layers, sizeof(MegaLayer) * kLayers));
     TTS_CUDA_TRY(cudaMemcpy(m.mega_layers, ml.data(), sizeof(MegaLayer) * kLayers, cudaMemcpyHostToDevice));
-    TTS_CUDA_TRY(cudaMalloc(&m.mega_bar, 2 * sizeof(unsigned int)));
     {  // exchange buffers of ar_mega2.cuh: zero tags never match (launch generations start at 1)
       const size_t nb = std::min<size_t>(B, 4);
       const size_t sizes[5] = {M2_REP * nb * kDim, M2_REP * nb * kDim, nb * 3072, M2_REP * nb * (kFF / 2),
@@ -147,7 +146,7 @@ void ar_load(tts_ctx *c, const char *path) {
       uint2 **ptrs[5] = {&m.ll_h, &m.ll_h2, &m.ll_qkv, &m.ll_m, &m.ll_att};
       for (int i = 0; i < 5; ++i) {
         m.ll_bytes[i] = sizes[i] * sizeof(uint2);
-        TTS_CUDA_TRY(cudaMalloc(ptrs[i], m.ll_bytes[i]));
+        TTS_CUDA_TRY(ctx_malloc(c, ptrs[i], m.ll_bytes[i]));
         TTS_CUDA_TRY(cudaMemset(*ptrs[i], 0, m.ll_bytes[i]));
       }
       m.mega_epoch = 0;
@@ -155,7 +154,7 @@ void ar_load(tts_ctx *c, const char *path) {
     const char *tr = getenv("TTS_MEGA_TRACE");
     if (tr && (tr[0] == '1' || tr[0] == '2')) {
       m.mega_dbg_mode = tr[0] - '0';
-      TTS_CUDA_TRY(cudaMalloc(&m.mega_dbg, kMegaDbgWords * sizeof(long long)));
+      TTS_CUDA_TRY(ctx_malloc(c, &m.mega_dbg, kMegaDbgWords * sizeof(long long)));
       TTS_CUDA_TRY(cudaMemset(m.mega_dbg, 0, kMegaDbgWords * sizeof(long long)));
     }
   }
@@ -166,22 +165,17 @@ void ar_free(tts_ctx *c) {
   ArState &s = c->ars;
   if (s.step_graph) cudaGraphExecDestroy(s.step_graph);
   s.step_graph = nullptr;
-  // device memory is released wholesale by cudaDeviceReset-free teardown in tts_free
+  // (device / pinned buffers belong to the context's allocation registry: tts_free -> ctx_free_all)
 }
 
 // ------------------------------------------------------------------------------------------
 template <typename WT>
 static void launch_gemv_t(tts_ctx *c, const Launcher &L, const GemvArgs &a) {
   const size_t smem = gemv_smem_bytes();
-  static bool attr_done[2][2] = {{false, false}, {false, false}};
   auto k1 = wsgemv_kernel<WT, 1>;
   auto k2 = wsgemv_kernel<WT, 2>;
-  const int wi = sizeof(WT) == 4 ? 0 : 1;
-  if (!attr_done[wi][0]) {
-    TTS_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    TTS_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr_done[wi][0] = true;
-  }
+  ensure_smem_attr(k1, smem);
+  ensure_smem_attr(k2, smem);
   const int G = c->num_sms;
   if ((a.N + G - 1) / G > GV_MAX_ROWS_PER_CTA) throw ArgError("gemv: too many rows per CTA");
   if (a.B == 1)
@@ -245,40 +239,12 @@ static void enqueue_step(tts_ctx *c, const Launcher &L, int B) {
   enqueue_lm_head(c, L, B);
 }
 
-// One decode step = one cooperative launch of the persistent kernel (ar_mega.cuh).
-template <typename WT>
-static void launch_mega_t(tts_ctx *c, int B, int n_past, int pos_id) {
-  ArModel &m = c->ar;
-  ArState &s = c->ars;
-  MegaArgs a{};
-  a.layers = (const MegaLayer *)m.mega_layers;
-  a.lnf_w = m.lnf_w; a.lnf_b = m.lnf_b; a.lm0_w = m.lm0_w; a.lm0_b = m.lm0_b; a.lm_b = m.lm_b; a.lm_w = m.lm_w;
-  a.mel_emb = m.mel_emb; a.mel_pos = m.mel_pos; a.tokens = s.d_tokens;
-  a.h = s.h; a.q = s.q; a.attn = s.attn; a.m = s.m; a.logits = s.logits; a.kc = s.kc; a.vc = s.vc;
-  a.dbg = m.mega_dbg;
-  a.bar = m.mega_bar; a.B = B; a.Bmax = s.Bmax; a.P = s.P; a.n_past = n_past; a.pos_id = pos_id;
-  static bool attr1 = false, attr2 = false;
-  void *args[] = {&a};
-  const size_t smem = mega_smem_bytes();
-  if (B == 1) {
-    auto k = ar_decode_mega_kernel<WT, 1>;
-    if (!attr1) { TTS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr1 = true; }
-    TTS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k, dim3(c->num_sms), dim3(MG_THREADS), args, smem, c->stream));
-  } else {
-    auto k = ar_decode_mega_kernel<WT, 2>;
-    if (!attr2) { TTS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr2 = true; }
-    TTS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k, dim3(c->num_sms), dim3(MG_THREADS), args, smem, c->stream));
-  }
-  c->launches += 1;
-}
-
 // Second generation (ar_mega2.cuh): tag-fused activation exchange, up to 4 candidates per weight stream.
 template <typename WT, int BT>
 static void launch_mega2_bt(tts_ctx *c, Mega2Args &a) {
   auto k = ar_decode_mega2_kernel<WT, BT>;
-  static bool attr = false;
   const size_t smem = mega2_smem_bytes<BT>();
-  if (!attr) { TTS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  ensure_smem_attr(k, smem);
   void *args[] = {&a};
   TTS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k, dim3(c->num_sms), dim3(M2_THREADS), args, smem, c->stream));
   c->launches += 1;
@@ -288,9 +254,8 @@ static void launch_mega2_bt(tts_ctx *c, Mega2Args &a) {
 template <int BT>
 static void launch_mega3_bt(tts_ctx *c, Mega2Args &a) {
   auto k = ar_decode_mega3_kernel<BT>;
-  static bool attr = false;
   const size_t smem = mega3_smem_bytes<BT>();
-  if (!attr) { TTS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); attr = true; }
+  ensure_smem_attr(k, smem);
   void *args[] = {&a};
   TTS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k, dim3(c->num_sms), dim3(M2_THREADS), args, smem, c->stream));
   c->launches += 1;
@@ -314,23 +279,13 @@ static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
   a.Bmax = s.Bmax; a.P = s.P; a.n_past = n_past; a.pos_id = pos_id;
   a.dbg = m.mega_dbg;
   a.dbg_mode = m.mega_dbg_mode;
-  {
-    static int nrep = -1;
-    if (nrep < 0) { const char *e = getenv("TTS_MEGA_REP"); nrep = e ? std::max(1, std::min(int(M2_REP), atoi(e))) : 2; }  // same-box A/B: 8 -> 726, 4 -> 680, 2 -> 665, 1 -> 692 us / step
-    a.nrep = nrep;
-    static int defer = -1;
-    if (defer < 0) { const char *e = getenv("TTS_MEGA_NODEFER"); defer = (e && e[0] == '1') ? 0 : 1; }
-    a.defer = defer;
-    static int spin = -1;
-    if (spin < 0) { const char *e = getenv("TTS_MEGA_SPIN"); spin = e ? atoi(e) : 0; }
-    a.poll_spin = spin;
-    static int kps = -1;
-    if (kps < 0) { const char *e = getenv("TTS_MEGA_KPS"); kps = e ? std::max(8, std::min(128, atoi(e))) : 128; }
-    a.keys_per_split = kps;
-    static int ef = -1;
-    if (ef < 0) { const char *e = getenv("TTS_MEGA_NOEVICT"); ef = (e && e[0] == '0') ? 1 : 0; }  // TTS_MEGA_NOEVICT=0 turns the hint ON; same-box A/B: 541 us with, 527 us without
-    a.evict_first = ef;
-  }
+  // settled by same-box A/B runs (profiles/r01_decode_*_ab.txt): 2 replicas of the all-to-all vectors,
+  // deferred ring-slot release, plain re-polls, one attention item per head, no L2 eviction hint
+  a.nrep = 2;
+  a.defer = 1;
+  a.poll_spin = 0;
+  a.keys_per_split = 128;
+  a.evict_first = 0;
   // up to 4 candidates ride on one weight stream; more candidates = one launch per group of 4
   // (the exchange buffers are reused: tags are unique per launch)
   for (int b0 = 0; b0 < B; b0 += 4) {
@@ -355,15 +310,15 @@ static void ensure_rows(tts_ctx *c, size_t rows) {
   if (rows <= s.rows_cap) return;
   for (void *p : {(void *)s.H, (void *)s.QKV, (void *)s.Z, (void *)s.Ahi, (void *)s.Alo, (void *)s.ATThi,
                   (void *)s.ATTlo, (void *)s.Mhi})
-    if (p) cudaFree(p);
-  TTS_CUDA_TRY(cudaMalloc(&s.H, rows * kDim * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.QKV, rows * 3072 * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.Z, rows * kDim * 4));
-  TTS_CUDA_TRY(cudaMalloc(&s.Ahi, rows * kDim * 2));
-  TTS_CUDA_TRY(cudaMalloc(&s.Alo, rows * kDim * 2));
-  TTS_CUDA_TRY(cudaMalloc(&s.ATThi, rows * kDim * 2));
-  TTS_CUDA_TRY(cudaMalloc(&s.ATTlo, rows * kDim * 2));
-  TTS_CUDA_TRY(cudaMalloc(&s.Mhi, rows * kFF * 2));
+    if (p) ctx_free(c, p);
+  TTS_CUDA_TRY(ctx_malloc(c, &s.H, rows * kDim * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.QKV, rows * 3072 * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.Z, rows * kDim * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.Ahi, rows * kDim * 2));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.Alo, rows * kDim * 2));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.ATThi, rows * kDim * 2));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.ATTlo, rows * kDim * 2));
+  TTS_CUDA_TRY(ctx_malloc(c, &s.Mhi, rows * kFF * 2));
   s.rows_cap = rows;
 }
 
@@ -468,24 +423,27 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
   if (s.n_past + 1 > s.P) throw ArgError("KV cache full (reference limit: 404 slots, main.cpp:794-797)", TTS_ELIMIT);
   if (pos_id < 0 || pos_id >= 608) throw ArgError("mel position id out of range (608 rows)", TTS_ELIMIT);
   const int B = s.B;
-  for (int b = 0; b < B; ++b) {
+  for (int b = 0; b < B; ++b)
     if (tokens[b] < 0 || tokens[b] >= kMelVocab) throw ArgError("mel token out of range");
-    s.h_tokens[b] = tokens[b];
-  }
+  // the pinned token / state words are read by copies queued on the stream (captured in the per-op
+  // graph): a back-to-back asynchronous step must not overwrite them before the previous one ran
+  const bool mega = c->use_mega && s.P <= 1024;
+  if (!sync_out && !mega) TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (int b = 0; b < B; ++b) s.h_tokens[b] = tokens[b];
   s.h_state[0] = s.n_past;
   s.h_state[1] = pos_id;
   const int launches_per_step = 2 + kLayers * 5;
   TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-  if (c->use_mega && s.P <= 1024) {
-    TTS_CUDA_TRY(cudaMemcpyAsync(s.d_tokens, s.h_tokens, B * 4, cudaMemcpyHostToDevice, c->stream));
-    if (!c->use_mega_v1) {
-      if (c->ar.dtype == TTS_DTYPE_F16) launch_mega2_t<__half>(c, B, s.n_past, pos_id);
-      else launch_mega2_t<float>(c, B, s.n_past, pos_id);
-    } else {
-      TTS_CUDA_TRY(cudaMemsetAsync(c->ar.mega_bar, 0, 2 * sizeof(unsigned int), c->stream));
-      if (c->ar.dtype == TTS_DTYPE_F16) launch_mega_t<__half>(c, B, s.n_past, pos_id);
-      else launch_mega_t<float>(c, B, s.n_past, pos_id);
+  if (mega) {
+    {  // tokens travel as kernel parameters (no pinned staging to race with an asynchronous caller)
+      TokenArgs ta{};
+      for (int b = 0; b < B; ++b) ta.tok[b] = tokens[b];
+      set_tokens_kernel<<<1, 64, 0, c->stream>>>(s.d_tokens, ta, B);
+      TTS_CUDA_TRY(cudaGetLastError());
+      c->launches += 1;
     }
+    if (c->ar.dtype == TTS_DTYPE_F16) launch_mega2_t<__half>(c, B, s.n_past, pos_id);
+    else launch_mega2_t<float>(c, B, s.n_past, pos_id);
     TTS_CUDA_TRY(cudaMemcpyAsync(s.h_logits, s.logits, size_t(B) * kMelVocab * 4, cudaMemcpyDeviceToHost, c->stream));
   } else if (c->use_graph) {
     if (!s.step_graph || s.step_graph_B != B) build_step_graph(c, B);
@@ -537,7 +495,9 @@ void ar_latents(tts_ctx *c, const int32_t *text, int T, const float *voice, cons
   const int chunk = std::max(1, std::min(B, 8192 / R));
   ensure_rows(c, size_t(chunk) * R);
   std::vector<int> pos(size_t(B) * 502, 0), h_codes(size_t(B) * n_mel), h_pos(size_t(B) * n_mel);
-  if (c->cfg.parity_quirks) {
+  // The quirk only exists where the reference itself runs (B <= 4: its KV / position buffers are
+  // sized for 4 candidates, main.cpp:794-797); beyond that every candidate gets positions 0..501.
+  if (c->cfg.parity_quirks && B <= 4) {
     const int per = 502 * B / 4;
     for (int i = 0; i < B; ++i)
       for (int cc = 0; cc < per; ++cc) {
@@ -553,11 +513,13 @@ void ar_latents(tts_ctx *c, const int32_t *text, int T, const float *voice, cons
       const int code = codes[size_t(b) * 502 + j];
       if (code < 0 || code >= kMelVocab) throw ArgError("mel code out of range");
       h_codes[size_t(b) * n_mel + j] = code;
-      h_pos[size_t(b) * n_mel + j] = pos[size_t(b) * 502 + j];
+      const int pj = pos[size_t(b) * 502 + j];
+      if (pj < 0 || pj >= 608) throw ArgError("mel position id out of range (608 rows)", TTS_ELIMIT);
+      h_pos[size_t(b) * n_mel + j] = pj;
     }
   if (!s.d_codes) {
-    TTS_CUDA_TRY(cudaMalloc(&s.d_codes, size_t(s.Bmax) * 502 * 4));
-    TTS_CUDA_TRY(cudaMalloc(&s.d_pos, size_t(s.Bmax) * 502 * 4));
+    TTS_CUDA_TRY(ctx_malloc(c, &s.d_codes, size_t(s.Bmax) * 502 * 4));
+    TTS_CUDA_TRY(ctx_malloc(c, &s.d_pos, size_t(s.Bmax) * 502 * 4));
   }
   Launcher L{c->stream, c->use_pdl, &c->launches};
   TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));

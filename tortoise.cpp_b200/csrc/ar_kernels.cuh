@@ -338,4 +338,12 @@ static __global__ void convert_kernel(const float *src, WT *dst, size_t n) {
   }
 }
 
+// tokens of one decode step, passed by value (max_batch <= 64)
+struct TokenArgs {
+  int tok[64];
+};
+static __global__ void set_tokens_kernel(int *dst, TokenArgs t, int n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = t.tok[threadIdx.x];
+}
+
 }  // namespace tts

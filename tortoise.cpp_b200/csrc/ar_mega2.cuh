@@ -1,9 +1,9 @@
-// ar_mega2.cuh -- AR decode step as one persistent kernel, second generation: the device-wide
-// barriers of ar_mega.cuh are gone.
+// ar_mega2.cuh -- AR decode step as one persistent kernel (f32 parity mode; also the shared
+// protocol pieces of ar_mega3.cuh / ar_mega4.cuh).  No device-wide barriers.
 //
-// Same math as ar_mega.cuh / wsgemv.cuh (reference graph autoregressive_graph(fake_inputs=false),
+// Same math as wsgemv.cuh (reference graph autoregressive_graph(fake_inputs=false),
 // main.cpp:2668-3029).  What changed, and why (measured with the in-kernel clock trace,
-// profiles/r01_decode_step.md): in the first generation a phase boundary cost 3000-4500 cycles
+// profiles/r01_decode_step.md): with device-wide barriers a phase boundary cost 3000-4500 cycles
 // (bar.sync -> MEMBAR.GPU + RED -> one thread polling the counter -> bar.sync -> the L2 round trip
 // that finally fetches the activations) and the LayerNorm prologue another 3000 (two more dependent
 // L2 round trips).  Here
@@ -33,9 +33,16 @@
 // Weight streaming is unchanged: a dedicated producer warp walks the whole step's weight slices
 // of this CTA, in consumption order, through a ring of 16 KB stages with 1-D TMA bulk copies.
 #pragma once
-#include "ar_mega.cuh"
+#include "ar_kernels.cuh"
+#include "wsgemv.cuh"
 
 namespace tts {
+
+struct MegaLayer {
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  const void *w_qkv, *w_proj, *w_fc, *w_proj2;
+  const float *b_qkv, *b_proj, *b_fc, *b_proj2;
+};
 
 constexpr int M2_CONSUMERS = 256;
 constexpr int M2_THREADS = M2_CONSUMERS + 128;  // + one warpgroup: warp 8 = weight-stream producer, warps 9-11 exit at once

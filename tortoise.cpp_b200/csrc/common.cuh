@@ -5,7 +5,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+#include <set>
 #include <string>
+#include <utility>
 
 namespace tts {
 
@@ -43,6 +46,21 @@ struct ArgError {
   int code;
   explicit ArgError(const std::string &m, int c = -1) : msg(m), code(c) {}
 };
+
+// Opt-in to > 48 KB of dynamic shared memory.  The attribute is per DEVICE, a process may own
+// contexts on several GPUs and C-ABI calls may come from several threads: remember (device, kernel).
+template <typename K>
+inline void ensure_smem_attr(K kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void *>> done;
+  int dev = 0;
+  TTS_CUDA_TRY(cudaGetDevice(&dev));
+  const std::pair<int, const void *> key(dev, reinterpret_cast<const void *>(kernel));
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(key)) return;
+  TTS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+  done.insert(key);
+}
 
 // ---- programmatic dependent launch (PDL) ----------------------------------------------
 // Every kernel in a stage's chain is launched with programmatic stream serialization so

@@ -72,7 +72,7 @@ static __half *upload_conv_w(tts_ctx *c, const Container &ct, const std::string 
   size_t n = 0;
   read_tensor_to_staging(c, ct, name, &n);
   __half *d = nullptr;
-  TTS_CUDA_TRY(cudaMalloc(&d, size_t(K) * OC * ICpad * 2));
+  TTS_CUDA_TRY(ctx_malloc(c, &d, size_t(K) * OC * ICpad * 2));
   conv_weight_kernel<<<1024, 256, 0, c->stream>>>(c->d_scratch, d, OC, IC, K, ICpad);
   TTS_CUDA_TRY(cudaGetLastError());
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -97,6 +97,7 @@ void diff_load(tts_ctx *c, const char *path) {
   Container ct;
   std::string err;
   if (!ct.open(path, err)) throw ArgError(err, TTS_EIO);
+  if (c->diff && c->diff->loaded) throw ArgError("diffusion model already loaded in this context");
   if (!c->diff) c->diff = new DiffModel();
   DiffModel &m = *c->diff;
   std::set<std::string> known;
@@ -107,8 +108,8 @@ void diff_load(tts_ctx *c, const char *path) {
   };
   auto planes = [&](const std::string &n, int N, int K, __half **hi, __half **lo) {
     known.insert(n);
-    TTS_CUDA_TRY(cudaMalloc(hi, size_t(N) * K * 2));
-    TTS_CUDA_TRY(cudaMalloc(lo, size_t(N) * K * 2));
+    TTS_CUDA_TRY(ctx_malloc(c, hi, size_t(N) * K * 2));
+    TTS_CUDA_TRY(ctx_malloc(c, lo, size_t(N) * K * 2));
     upload_planes(c, ct, n, N, K, *hi, *lo);
   };
   auto load_attn = [&](const std::string &p, DAttn &a) {
@@ -120,9 +121,9 @@ void diff_load(tts_ctx *c, const char *path) {
     a.b_proj = f32(p + "proj_out.bias", {1024});
     a.relbias = f32(p + "relative_pos_embeddings.relative_attention_bias.weight", {16, 32});
   };
-  TTS_CUDA_TRY(cudaMalloc(&m.emb_hi, size_t(16) * 2048 * 1024 * 2));
-  TTS_CUDA_TRY(cudaMalloc(&m.emb_lo, size_t(16) * 2048 * 1024 * 2));
-  TTS_CUDA_TRY(cudaMalloc(&m.emb_b, size_t(16) * 2048 * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &m.emb_hi, size_t(16) * 2048 * 1024 * 2));
+  TTS_CUDA_TRY(ctx_malloc(c, &m.emb_lo, size_t(16) * 2048 * 1024 * 2));
+  TTS_CUDA_TRY(ctx_malloc(c, &m.emb_b, size_t(16) * 2048 * 4));
   auto load_res = [&](const std::string &p, DRes &r, int idx) {
     r.gn1_w = f32(p + "in_layers.0.weight", {1024});
     r.gn1_b = f32(p + "in_layers.0.bias", {1024});
@@ -133,7 +134,7 @@ void diff_load(tts_ctx *c, const char *path) {
                   m.emb_lo + size_t(idx) * 2048 * 1024);
     float *eb = f32(p + "emb_layers.1.bias", {2048});
     TTS_CUDA_TRY(cudaMemcpy(m.emb_b + size_t(idx) * 2048, eb, 2048 * 4, cudaMemcpyDeviceToDevice));
-    cudaFree(eb);
+    ctx_free(c, eb);
     r.gn2_w = f32(p + "out_layers.0.weight", {1024});
     r.gn2_b = f32(p + "out_layers.0.bias", {1024});
     r.w_out3 = convw(p + "out_layers.3.weight", 1024, 1024, 3, 1024);
@@ -176,54 +177,54 @@ void diff_load(tts_ctx *c, const char *path) {
 
 void diff_free(tts_ctx *c) {
   if (c->diff) {
-    if (c->diff->h_pin) cudaFreeHost(c->diff->h_pin);
-    delete c->diff;
+    if (c->diff->step_graph) cudaGraphExecDestroy(c->diff->step_graph);
+    delete c->diff;  // its buffers belong to the context's allocation registry (tts_free)
     c->diff = nullptr;
   }
 }
 
 template <typename T>
-static void grow(T **p, size_t n) {
-  if (*p) cudaFree(*p);
-  TTS_CUDA_TRY(cudaMalloc(p, n * sizeof(T)));
+static void grow(tts_ctx *c, T **p, size_t n) {
+  if (*p) ctx_free(c, *p);
+  TTS_CUDA_TRY(ctx_malloc(c, p, n * sizeof(T)));
 }
 
 static void ensure_buffers(tts_ctx *c, int S, int steps) {
   DiffModel &m = *c->diff;
   if (S > m.capS) {
     const size_t s2 = size_t(2) * S;
-    grow(&m.X, s2 * kDim);
-    grow(&m.CW, s2 * kDim);
-    grow(&m.CE, s2 * kDim);
-    grow(&m.H1, s2 * kDim);
-    grow(&m.QKV, s2 * 3072);
-    grow(&m.OUT, s2 * 200);
-    grow(&m.INP, size_t(S) * kDim);
-    grow(&m.stats, size_t(2) * 32 * 2);
-    grow(&m.x_dev, size_t(100) * S);
-    grow(&m.lat_dev, size_t(S) * kDim);
-    grow(&m.A16, size_t(2) * (S + 2) * kDim);
-    grow(&m.CAT16, size_t(2) * (S + 2) * 2048);
-    grow(&m.XIN16, size_t(S + 2) * 128);
-    grow(&m.ATThi, s2 * kDim);
-    grow(&m.ATTlo, s2 * kDim);
-    grow(&m.rpb, size_t(S) + 8);
-    grow(&m.up_idx, size_t(S));
-    if (!m.d_step) TTS_CUDA_TRY(cudaMalloc(&m.d_step, 4));
-    if (!m.gn_partial) TTS_CUDA_TRY(cudaMalloc(&m.gn_partial, size_t(2) * 32 * 64 * 2 * sizeof(double)));
+    grow(c, &m.X, s2 * kDim);
+    grow(c, &m.CW, s2 * kDim);
+    grow(c, &m.CE, s2 * kDim);
+    grow(c, &m.H1, s2 * kDim);
+    grow(c, &m.QKV, s2 * 3072);
+    grow(c, &m.OUT, s2 * 200);
+    grow(c, &m.INP, size_t(S) * kDim);
+    grow(c, &m.stats, size_t(2) * 32 * 2);
+    grow(c, &m.x_dev, size_t(100) * S);
+    grow(c, &m.lat_dev, size_t(S) * kDim);
+    grow(c, &m.A16, size_t(2) * (S + 2) * kDim);
+    grow(c, &m.CAT16, size_t(2) * (S + 2) * 2048);
+    grow(c, &m.XIN16, size_t(S + 2) * 128);
+    grow(c, &m.ATThi, s2 * kDim);
+    grow(c, &m.ATTlo, s2 * kDim);
+    grow(c, &m.rpb, size_t(S) + 8);
+    grow(c, &m.up_idx, size_t(S));
+    if (!m.d_step) TTS_CUDA_TRY(ctx_malloc(c, &m.d_step, 4));
+    if (!m.gn_partial) TTS_CUDA_TRY(ctx_malloc(c, &m.gn_partial, size_t(2) * 32 * 64 * 2 * sizeof(double)));
     m.partial_src = nullptr;  // buffers moved: no tensor has fused statistics
     if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; m.graph_S = -1; }
     m.capS = S;
     m.cond_L = m.cond_S = -1;
   }
   if (steps > m.capSteps) {
-    grow(&m.TE, size_t(steps) * kDim);
-    grow(&m.T0, size_t(steps) * kDim);
-    grow(&m.TEMB, size_t(steps) * kDim);
-    grow(&m.EMB, size_t(steps) * 16 * 2048);
-    grow(&m.P_hi, size_t(steps) * kDim);
-    grow(&m.P_lo, size_t(steps) * kDim);
-    grow(&m.coefs, size_t(steps));
+    grow(c, &m.TE, size_t(steps) * kDim);
+    grow(c, &m.T0, size_t(steps) * kDim);
+    grow(c, &m.TEMB, size_t(steps) * kDim);
+    grow(c, &m.EMB, size_t(steps) * 16 * 2048);
+    grow(c, &m.P_hi, size_t(steps) * kDim);
+    grow(c, &m.P_lo, size_t(steps) * kDim);
+    grow(c, &m.coefs, size_t(steps));
     if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; m.graph_S = -1; }
     m.capSteps = steps;
   }
@@ -274,11 +275,7 @@ static void attn_block(tts_ctx *c, const Launcher &L, const DAttn &a, float *x, 
   DiffModel &m = *c->diff;
   gn(c, L, x, a.n_w, a.n_b, nullptr, m.A16, nullptr, nseq, T, 0);
   conv(c, L, m.A16, a.w_qkv, a.b_qkv, m.QKV, nseq, T, kDim, 3072, 1, 3072, E_BIAS);
-  static bool da_attr = false;
-  if (!da_attr) {
-    TTS_CUDA_TRY(cudaFuncSetAttribute(diff_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DA_SMEM)));
-    da_attr = true;
-  }
+  ensure_smem_attr(diff_attn_kernel, DA_SMEM);
   L(diff_attn_kernel, dim3((T + DA_Q - 1) / DA_Q, kHeads, nseq), dim3(DA_THREADS), DA_SMEM, (const float *)m.QKV,
     (const float *)a.relbias, (const int *)m.rpb, m.ATThi, m.ATTlo, T);
   tg(c, L, m.ATThi, m.ATTlo, a.proj_hi, a.proj_lo, a.b_proj, x, nseq * T, kDim, kDim, kDim, kDim, E_BIAS_RESID,
@@ -348,8 +345,8 @@ static void run_denoiser(tts_ctx *c, const Launcher &L, int nseq, int S, const f
 static float *pin(tts_ctx *c, size_t bytes) {
   DiffModel &m = *c->diff;
   if (m.h_pin_bytes < bytes) {
-    if (m.h_pin) cudaFreeHost(m.h_pin);
-    TTS_CUDA_TRY(cudaMallocHost(&m.h_pin, bytes));
+    if (m.h_pin) ctx_free_host(c, m.h_pin);
+    TTS_CUDA_TRY(ctx_malloc_host(c, &m.h_pin, bytes));
     m.h_pin_bytes = bytes;
   }
   return m.h_pin;
@@ -414,9 +411,9 @@ void diff_begin(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, co
   // noise: block 0 = initial x, block i+1 = the draw of step i (always drawn, used unless last)
   // (the graph embeds this pointer: reallocation drops the captured graph)
   if (m.noise_cap < size_t(n_steps + 1) * nx) {
-    if (m.noise_dev) cudaFree(m.noise_dev);
+    if (m.noise_dev) ctx_free(c, m.noise_dev);
     m.noise_dev = nullptr;
-    TTS_CUDA_TRY(cudaMalloc(&m.noise_dev, size_t(n_steps + 1) * nx * 4));
+    TTS_CUDA_TRY(ctx_malloc(c, &m.noise_dev, size_t(n_steps + 1) * nx * 4));
     m.noise_cap = size_t(n_steps + 1) * nx;
     if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; m.graph_S = -1; }
   }

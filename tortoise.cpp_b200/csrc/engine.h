@@ -4,10 +4,12 @@
 #include <cuda_runtime.h>
 
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
 #include "../../include/tortoise_b200.h"
+#include "common.cuh"
 
 namespace tts {
 
@@ -45,8 +47,7 @@ struct ArModel {
   void *lm_w;  // [8194][1024]
   float *text_emb, *text_pos, *mel_emb, *mel_pos;
   size_t decode_weight_bytes = 0;
-  void *mega_layers = nullptr;   // device MegaLayer[30] (ar_mega.cuh)
-  unsigned int *mega_bar = nullptr;
+  void *mega_layers = nullptr;   // device MegaLayer[30] (ar_mega2.cuh)
   long long *mega_dbg = nullptr;  // device trace buffer (TTS_MEGA_TRACE=1|2)
   int mega_dbg_mode = 0;
   // (value, tag) exchange buffers of the second-generation persistent step (ar_mega2.cuh)
@@ -92,7 +93,6 @@ struct tts_ctx {
   bool use_pdl = true;
   bool use_mega = true;   // persistent single-kernel decode step (TTS_NO_MEGA=1 -> per-op graph path)
   bool use_mega_v2 = false;  // TTS_MEGA_V2=1: CUDA-core GEMV phases also for f16 weights (default: tensor-core ar_mega3.cuh)
-  bool use_mega_v1 = false;  // TTS_MEGA_V1=1: first-generation persistent step (grid barriers), for A/B
   tts::ArModel ar;
   tts::ArState ars;
   tts::DiffModel *diff = nullptr;
@@ -101,9 +101,45 @@ struct tts_ctx {
   size_t staging_bytes = 0;
   float *d_scratch = nullptr;    // device scratch for load-time conversion
   size_t d_scratch_bytes = 0;
+  // every device / pinned-host allocation of this context (ctx_malloc / ctx_malloc_host): released
+  // by tts_free, so creating and destroying engines in one process does not leak
+  std::set<void *> dev_allocs, host_allocs;
 };
 
 namespace tts {
+// ---- context-owned memory ------------------------------------------------------------------
+template <typename T>
+inline cudaError_t ctx_malloc(tts_ctx *c, T **p, size_t bytes) {
+  void *q = nullptr;
+  const cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+  if (e == cudaSuccess) c->dev_allocs.insert(q);
+  *p = static_cast<T *>(q);
+  return e;
+}
+template <typename T>
+inline cudaError_t ctx_malloc_host(tts_ctx *c, T **p, size_t bytes) {
+  void *q = nullptr;
+  const cudaError_t e = cudaMallocHost(&q, bytes ? bytes : 1);
+  if (e == cudaSuccess) c->host_allocs.insert(q);
+  *p = static_cast<T *>(q);
+  return e;
+}
+inline void ctx_free(tts_ctx *c, const void *p) {
+  if (!p) return;
+  c->dev_allocs.erase(const_cast<void *>(p));
+  cudaFree(const_cast<void *>(p));
+}
+inline void ctx_free_host(tts_ctx *c, const void *p) {
+  if (!p) return;
+  c->host_allocs.erase(const_cast<void *>(p));
+  cudaFreeHost(const_cast<void *>(p));
+}
+inline void ctx_free_all(tts_ctx *c) {
+  for (void *p : c->dev_allocs) cudaFree(p);
+  for (void *p : c->host_allocs) cudaFreeHost(p);
+  c->dev_allocs.clear();
+  c->host_allocs.clear();
+}
 // implemented in ar.cu
 void ar_load(tts_ctx *c, const char *path);
 void ar_prefill(tts_ctx *c, const int32_t *text, int T, const float *voice, int B, float *logits_out);
@@ -113,8 +149,6 @@ void ar_latents(tts_ctx *c, const int32_t *text, int T, const float *voice, cons
 void ar_bench_gemv(tts_ctx *c, int op, int B, int iters, float *ms, double *bytes);
 void ar_bench_step(tts_ctx *c, int iters, float *ms, double *bytes);
 void ar_free(tts_ctx *c);
-void bench_stream(tts_ctx *c, int mode, int stage_bytes, int stages, size_t bytes_per_cta, int iters, float *ms,
-                  double *bytes);
 // implemented in diffusion.cu / vocoder.cu
 void diff_load(tts_ctx *c, const char *path);
 void diff_eps(tts_ctx *c, const float *latents, int L, const float *x, int S, int timestep, int cond_free,

@@ -44,10 +44,8 @@ static inline int launch_gemm(const Launcher &L, const TGemmArgs &g_in) {
     // GEMMs are small (M = 2S ~ 400 rows) and latency-bound; 4 stages when lo planes double a stage
     const bool deep = !alo && !wlo;
     auto go = [&](auto kern, int BN, int stages) {
-      TTS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        int(tc5_smem_bytes(BN, stages, true, true) > 227 * 1024
-                                                ? tc5_smem_bytes(BN, stages, alo, wlo)
-                                                : tc5_smem_bytes(BN, stages, true, true))));
+      ensure_smem_attr(kern, tc5_smem_bytes(BN, stages, true, true) > 227 * 1024 ? tc5_smem_bytes(BN, stages, alo, wlo)
+                                                                                  : tc5_smem_bytes(BN, stages, true, true));
       L(kern, dim3((g.N + BN - 1) / BN, mt, nseq), dim3(T5_THREADS), tc5_smem_bytes(BN, stages, alo, wlo), g);
     };
     if (bn64) {
@@ -59,12 +57,7 @@ static inline int launch_gemm(const Launcher &L, const TGemmArgs &g_in) {
     }
     return want_gn ? mt : 0;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    TTS_CUDA_TRY(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(tgemm_smem_bytes())));
-    attr_done = true;
-  }
+  ensure_smem_attr(tgemm_kernel, tgemm_smem_bytes());
   dim3 grid((g.N + TG_BN - 1) / TG_BN, (g.M + TG_BM - 1) / TG_BM);
   L(tgemm_kernel, grid, dim3(128), tgemm_smem_bytes(), g);
   return 0;

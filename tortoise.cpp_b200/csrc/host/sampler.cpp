@@ -190,7 +190,9 @@ int sample_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev,
   // (the fast path draws from the generator only after it has decided not to defer)
   const int s = sample_fast_one(r, logits_row, prev, n_prev, logprob);
   if (s >= 0) return s;
-  if (logprob) *logprob = 0.f;
+  // the literal path does not track the picked probability: report "unknown" (NaN) so that the
+  // caller's mean-log-prob score skips this step instead of counting a perfect 0
+  if (logprob) *logprob = std::numeric_limits<float>::quiet_NaN();
   return sample_literal_one(r, logits_row, prev, n_prev);
 }
 

@@ -47,9 +47,20 @@ bool Container::open(const std::string &p, std::string &err) {
     std::string name(name_len, 0);
     if (fread(&name[0], 1, name_len, f) != size_t(name_len)) { err = "truncated record"; fclose(f); return false; }
     t.nelem = 1;
-    for (int d : t.ne) t.nelem *= size_t(d);
+    bool bad_dim = false;
+    for (int d : t.ne) {
+      // a zero / negative dim, or a product that cannot fit the file, is a malformed record (a
+      // negative dim would otherwise wrap the size_t product past the bounds check below)
+      if (d <= 0 || t.nelem > size_t(fsize) / size_t(d)) { bad_dim = true; break; }
+      t.nelem *= size_t(d);
+    }
+    if (bad_dim) {
+      err = "tensor '" + name + "' has an invalid shape in '" + p + "'";
+      fclose(f);
+      return false;
+    }
     t.offset = size_t(ftell(f));
-    if (t.offset + t.nelem * 4 > size_t(fsize)) {
+    if (t.nelem > (size_t(fsize) - t.offset) / 4) {
       err = "tensor '" + name + "' runs past the end of '" + p + "'";
       fclose(f);
       return false;
@@ -64,13 +75,13 @@ bool Container::open(const std::string &p, std::string &err) {
 
 static void ensure_staging(tts_ctx *c, size_t bytes) {
   if (c->staging_bytes < bytes) {
-    if (c->staging) cudaFreeHost(c->staging);
-    TTS_CUDA_TRY(cudaMallocHost(&c->staging, bytes));
+    if (c->staging) ctx_free_host(c, c->staging);
+    TTS_CUDA_TRY(ctx_malloc_host(c, &c->staging, bytes));
     c->staging_bytes = bytes;
   }
   if (c->d_scratch_bytes < bytes) {
-    if (c->d_scratch) cudaFree(c->d_scratch);
-    TTS_CUDA_TRY(cudaMalloc(&c->d_scratch, bytes));
+    if (c->d_scratch) ctx_free(c, c->d_scratch);
+    TTS_CUDA_TRY(ctx_malloc(c, &c->d_scratch, bytes));
     c->d_scratch_bytes = bytes;
   }
 }
@@ -115,7 +126,7 @@ float *upload_f32(tts_ctx *c, const Container &ct, const std::string &name, cons
   size_t n = 0;
   read_tensor_to_staging(c, ct, name, &n);
   float *d = nullptr;
-  TTS_CUDA_TRY(cudaMalloc(&d, n * 4));
+  TTS_CUDA_TRY(ctx_malloc(c, &d, n * 4));
   TTS_CUDA_TRY(cudaMemcpyAsync(d, c->d_scratch, n * 4, cudaMemcpyDeviceToDevice, c->stream));
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   return d;

@@ -379,17 +379,9 @@ static inline int launch_tc5v2(const Launcher &L, TGemmArgs g) {
   if (!want_gn) g.gn_partial = nullptr;
   g.gn_mtiles = mt * csz;
   const size_t stage_bytes = size_t(T6_PLANE) * ((alo ? 2 : 1) + (wlo ? 2 : 1));
-  size_t budget = 226 * 1024 - 1024 - T6_CTRL;
-  {
-    // Experiment knob (default off): cap the ring so two CTAs fit on an SM (with -DT6_MIN_CTAS=2 for
-    // the registers) and the next kernel of the chain can become resident under programmatic
-    // dependent launch.  Measured, 20 sampling steps on one box: 30.4 ms uncapped, 30.7 ms at 100 KB,
-    // 31.5 ms at 72 KB, 29.6 ms at 100 KB without PDL -- residency is not what serialises the chain.
-    static long cap_kb = -1;
-    if (cap_kb < 0) { const char *e = getenv("TTS_TC5_SMEM_KB"); cap_kb = e ? atol(e) : 0; }
-    const size_t cap = size_t(cap_kb) * 1024;
-    if (cap > 0 && cap / stage_bytes >= 2 && cap >= size_t(T6_BM) * T6_RED_LD * 4) budget = std::min(budget, cap);
-  }
+  const size_t budget = 226 * 1024 - 1024 - T6_CTRL;
+  // (capping the ring so that two CTAs fit on an SM -- the next kernel of the chain resident under PDL --
+  // measured no gain: 30.4 ms uncapped vs 30.7 / 31.5 ms at 100 / 72 KB for 20 sampling steps)
   int stages = int(budget / stage_bytes);
   if (stages > T6_MAX_STAGES) stages = T6_MAX_STAGES;
   const int per_rank = (iters + csz - 1) / csz;
@@ -397,11 +389,7 @@ static inline int launch_tc5v2(const Launcher &L, TGemmArgs g) {
   size_t smem = stages * stage_bytes;
   if (smem < size_t(T6_BM) * T6_RED_LD * 4) smem = size_t(T6_BM) * T6_RED_LD * 4;  // partial tile
   smem += 1024 + T6_CTRL;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TTS_CUDA_TRY(cudaFuncSetAttribute(tc5v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_done = true;
-  }
+  ensure_smem_attr(tc5v2_kernel, 226 * 1024);
   const uint64_t a_rows = uint64_t(nseq) * (g.T + 2 * g.halo);
   const CUtensorMap mAhi = tc5v2_map(g.Ahi, a_rows, g.K, g.lda);
   const CUtensorMap mAlo = alo ? tc5v2_map(g.Alo, a_rows, g.K, g.lda) : mAhi;

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "engine.h"
+#include "../../include/tortoise_b200_bench.h"
 
 static std::string g_last_error;
 static std::mutex g_err_mu;
@@ -71,7 +72,6 @@ int tts_init(const tts_config *cfg, tts_ctx **out) {
   c->use_pdl = !(ep && ep[0] == '1');
   const char *em = getenv("TTS_NO_MEGA");
   c->use_mega = !(em && em[0] == '1');
-  { const char *e1 = getenv("TTS_MEGA_V1"); c->use_mega_v1 = e1 && e1[0] == '1'; }
   { const char *e2 = getenv("TTS_MEGA_V2"); c->use_mega_v2 = e2 && e2[0] == '1'; }
   try {
     TTS_CUDA_TRY(cudaSetDevice(cfg->device));
@@ -93,9 +93,7 @@ void tts_free(tts_ctx *c) {
   tts::ar_free(c);
   tts::diff_free(c);
   tts::voc_free(c);
-  // Per-tensor allocations are owned by the context's lifetime; release them in bulk.
-  if (c->staging) cudaFreeHost(c->staging);
-  if (c->d_scratch) cudaFree(c->d_scratch);
+  tts::ctx_free_all(c);  // every device / pinned allocation made through ctx_malloc*
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
@@ -154,13 +152,6 @@ int tts_bench_gemv(tts_ctx *c, int32_t op, int32_t B, int32_t iters, float *ms, 
 
 int tts_bench_decode_step(tts_ctx *c, int32_t iters, float *ms, double *bytes) {
   TTS_API_BODY(c, if (!ms || !bytes) throw tts::ArgError("bad argument"); tts::ar_bench_step(c, iters, ms, bytes))
-}
-
-int tts_bench_stream(tts_ctx *c, int32_t mode, int32_t stage_bytes, int32_t stages, int64_t bytes_per_cta, int32_t iters,
-                     float *ms, double *bytes) {
-  TTS_API_BODY(c, if (!ms || !bytes || stage_bytes % 16 || stages < 1 || bytes_per_cta % stage_bytes || size_t(stages) * stage_bytes > 200 * 1024)
-                      throw tts::ArgError("bad argument");
-               tts::bench_stream(c, mode, stage_bytes, stages, size_t(bytes_per_cta), iters, ms, bytes))
 }
 
 }  // extern "C"

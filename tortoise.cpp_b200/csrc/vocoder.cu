@@ -161,6 +161,7 @@ void voc_load(tts_ctx *c, const char *path) {
   Container ct;
   std::string err;
   if (!ct.open(path, err)) throw ArgError(err, TTS_EIO);
+  if (c->voc && c->voc->loaded) throw ArgError("vocoder model already loaded in this context");
   if (!c->voc) c->voc = new VocModel();
   VocModel &m = *c->voc;
   std::set<std::string> known;
@@ -175,7 +176,7 @@ void voc_load(tts_ctx *c, const char *path) {
     size_t nel = 0;
     read_tensor_to_staging(c, ct, n, &nel);
     __half *d = nullptr;
-    TTS_CUDA_TRY(cudaMalloc(&d, size_t(K) * OC * ICpad * 2));
+    TTS_CUDA_TRY(ctx_malloc(c, &d, size_t(K) * OC * ICpad * 2));
     conv_weight_kernel<<<1024, 256, 0, c->stream>>>(c->d_scratch, d, OC, IC, K, ICpad);
     TTS_CUDA_TRY(cudaGetLastError());
     TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -217,16 +218,15 @@ void voc_load(tts_ctx *c, const char *path) {
 
 void voc_free(tts_ctx *c) {
   if (c->voc) {
-    if (c->voc->h_pin) cudaFreeHost(c->voc->h_pin);
-    delete c->voc;
+    delete c->voc;  // its buffers belong to the context's allocation registry (tts_free)
     c->voc = nullptr;
   }
 }
 
 template <typename T>
-static void vgrow(T **p, size_t n) {
-  if (*p) cudaFree(*p);
-  TTS_CUDA_TRY(cudaMalloc(p, n * sizeof(T)));
+static void vgrow(tts_ctx *c, T **p, size_t n) {
+  if (*p) ctx_free(c, *p);
+  TTS_CUDA_TRY(ctx_malloc(c, p, n * sizeof(T)));
 }
 
 static void vtg(tts_ctx *c, const Launcher &L, const __half *X16, const __half *W, const float *bias, float *C, int M,
@@ -242,20 +242,20 @@ void voc_run(tts_ctx *c, const float *mel, int S, const float *noise, float *aud
   const int N0 = S + 10;
   const size_t Tmax = size_t(N0) * 256;
   if (N0 > m.capN0) {
-    vgrow(&m.mel_dev, size_t(100) * S + 16);
-    vgrow(&m.noise_dev, size_t(N0) * 64);
-    vgrow(&m.C, size_t(N0) * 64);
-    vgrow(&m.CO, size_t(N0) * 64);
-    vgrow(&m.KT, size_t(N0) * 24576);
-    vgrow(&m.BT, size_t(N0) * 256);
-    vgrow(&m.X, Tmax * 32);
-    vgrow(&m.X2, Tmax * 32);
-    vgrow(&m.Y, Tmax * 32);
-    vgrow(&m.audio, Tmax);
-    vgrow(&m.MEL16, size_t(N0 + 4) * 128);
-    vgrow(&m.C16, size_t(N0 + 2) * 64);
-    vgrow(&m.Z16, size_t(N0 + 6) * 64);
-    vgrow(&m.A16, (Tmax + 2 * VOC_HALO) * 32);
+    vgrow(c, &m.mel_dev, size_t(100) * S + 16);
+    vgrow(c, &m.noise_dev, size_t(N0) * 64);
+    vgrow(c, &m.C, size_t(N0) * 64);
+    vgrow(c, &m.CO, size_t(N0) * 64);
+    vgrow(c, &m.KT, size_t(N0) * 24576);
+    vgrow(c, &m.BT, size_t(N0) * 256);
+    vgrow(c, &m.X, Tmax * 32);
+    vgrow(c, &m.X2, Tmax * 32);
+    vgrow(c, &m.Y, Tmax * 32);
+    vgrow(c, &m.audio, Tmax);
+    vgrow(c, &m.MEL16, size_t(N0 + 4) * 128);
+    vgrow(c, &m.C16, size_t(N0 + 2) * 64);
+    vgrow(c, &m.Z16, size_t(N0 + 6) * 64);
+    vgrow(c, &m.A16, (Tmax + 2 * VOC_HALO) * 32);
     m.capN0 = N0;
   }
   Launcher L{c->stream, c->use_pdl, &c->launches};
@@ -304,8 +304,8 @@ void voc_run(tts_ctx *c, const float *mel, int S, const float *noise, float *aud
   const int n_out = Tlen - 6;
   vtg(c, L, m.A16, m.post_w, m.post_b, m.audio, n_out, 1, 32, 1, E_BIAS, 7, 1, 0, 0, n_out);
   if (m.h_pin_bytes < size_t(n_out) * 4) {
-    if (m.h_pin) cudaFreeHost(m.h_pin);
-    TTS_CUDA_TRY(cudaMallocHost(&m.h_pin, size_t(n_out) * 4));
+    if (m.h_pin) ctx_free_host(c, m.h_pin);
+    TTS_CUDA_TRY(ctx_malloc_host(c, &m.h_pin, size_t(n_out) * 4));
     m.h_pin_bytes = size_t(n_out) * 4;
   }
   TTS_CUDA_TRY(cudaMemcpyAsync(m.h_pin, m.audio, size_t(n_out) * 4, cudaMemcpyDeviceToHost, c->stream));
