@@ -80,6 +80,20 @@ int tts_ar_step(tts_ctx *ctx, const int32_t *tokens_B, int32_t pos_id, float *lo
 int tts_ar_step_dev(tts_ctx *ctx, const int32_t *tokens_B, int32_t pos_id,
                     const float **logits_dev);
 
+/* The same step with the reference's per-step D2H of 8194 floats per candidate (main.cpp:4767)
+ * replaced by a device-side pre-selection: vals_out / idx_out [B][TTS_AR_TOPK] receive the
+ * TTS_AR_TOPK largest logits of every candidate as unsorted (value, index) pairs (ties at the
+ * threshold: lowest indices first), flags_out[B] != 0 marks a candidate whose row must be fetched
+ * with tts_ar_logits instead (more than 256 ties at the threshold).  64 entries are enough for the
+ * host sampler to reproduce process_logits_and_sample bit-exactly (tts_host_sample_sparse proves
+ * it per call or asks for the full row). */
+#define TTS_AR_TOPK 64
+int tts_ar_step_topk(tts_ctx *ctx, const int32_t *tokens_B, int32_t pos_id, float *vals_out, int32_t *idx_out,
+                     int32_t *flags_out);
+
+/* full logits [B][8194] of the last tts_ar_prefill / tts_ar_step* call (blocking) */
+int tts_ar_logits(tts_ctx *ctx, float *logits_out);
+
 /* Replaces the latent pass, autoregressive_latent_graph + compute (main.cpp:5280-5352):
  * codes is [B][502] (8192, 500 codes, 8193 as built by apply_padding main.cpp:4510);
  * out is [B][500][1024] (lm_head.0-normalised hidden state of mel positions 0..499).

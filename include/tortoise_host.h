@@ -50,6 +50,14 @@ int tts_host_split_text(const char *in, int max_chars, int32_t *spans_out, int c
  *      the post-processed distribution (extension used for candidate selection). -------- */
 int tts_host_sample(tts_rng *r, const float *logits, const int32_t *prev, int n_prev, int B, int32_t *samples_out,
                     float *logprob_out);
+/* The same sampler for ONE candidate fed with the device-side pre-selection of tts_ar_step_topk:
+ * n (value, index) pairs = the n largest raw logits of the row.  Returns 0 and the sample when the
+ * result is provably the one tts_host_sample gives on the full row (bit-exact, same RNG draws);
+ * returns 1 WITHOUT touching the generator when it cannot show that (threshold too close to the
+ * cut, ties among survivors): the caller then fetches the row (tts_ar_logits) and uses
+ * tts_host_sample.  <0: bad argument. */
+int tts_host_sample_sparse(tts_rng *r, const float *vals, const int32_t *idx, int n, const int32_t *prev, int n_prev,
+                           int32_t *sample_out, float *logprob_out);
 /* literal (slow) restatement of the same function; used to cross-check the fast path */
 int tts_host_sample_reference_order(tts_rng *r, const float *logits, const int32_t *prev, int n_prev, int B,
                                     int32_t *samples_out);
@@ -76,7 +84,9 @@ typedef struct tts_ar_options {
                                were sampled, then forced (length decoupled from the sampler)  */
   int32_t per_candidate_stop; /* 0 = reference rule: run until ALL candidates emit 8193 in
                                the same step (main.cpp:5206-5222); 1 = each stops on its own   */
-  int32_t reserved;
+  int32_t full_logits;      /* 1 = copy all 8194 logits per candidate to the host every step like the
+                               reference (main.cpp:4767); 0 = device-side top-64 pre-selection
+                               (tts_ar_step_topk + tts_host_sample_sparse; identical samples)   */
 } tts_ar_options;
 
 /* autoregressive() (main.cpp:5042-5367).  codes_out [B][500] (after apply_padding, without

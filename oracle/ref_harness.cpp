@@ -13,7 +13,7 @@
 // Usage (cwd must contain ../models/{tokenizer.json,ggml-*.bin} exactly like ./tortoise):
 //   ref_harness shapes  <out.json>                    tensor name/shape manifest of the 3 files
 //   ref_harness tokenize <text>                        prints "255,<ids>,0"
-//   ref_harness ar   <text> <voice.bin> <B> <seed> <outdir> [max_computes]
+//   ref_harness ar   <text> <voice.bin> <B> <seed> <outdir> [max_computes|-1] [force_len]
 //   ref_harness diff <latents.f32> <seed> <outdir> [max_computes]
 //   ref_harness voc  <mel.f32> <seed> <outdir>
 //   ref_harness full <text> <voice.bin> <seed> <outdir>   (== ./tortoise, with dumps + timings)
@@ -38,6 +38,12 @@ static int g_get_count = 0;
 static double g_compute_seconds = 0;
 static std::vector<double> g_compute_times;
 static bool g_dump_all_logits = true;
+// forced-length AR runs (long-context goldens): while fewer than g_force_len logit rows have been
+// read back, the stop token's logit (8193) is replaced by -1e30 IN TRANSIT, after the true row was
+// dumped -- the reference's code is untouched, its sampler just never sees a winning stop logit.
+// Mirrors tts_ar_options.forced_codes of our own stage driver.
+static int g_force_len = 0;
+static int g_batch = 1;
 
 static void write_file(const std::string &path, const void *p, size_t n) {
   FILE *f = fopen(path.c_str(), "wb");
@@ -80,6 +86,8 @@ static void tensor_get(const struct ggml_tensor *t, void *data, size_t offset, s
     if (g_stage == "ar" && !g_dump_all_logits && g_get_count > 4) dump = false;
     if (dump) write_file(name, data, size);
   }
+  if (g_stage == "ar" && g_force_len > 0 && size == size_t(g_batch) * 8194 * 4 && g_get_count < g_force_len)
+    for (int b = 0; b < g_batch; ++b) static_cast<float *>(data)[size_t(b) * 8194 + 8193] = -1e30f;
   g_get_count++;
   report_and_exit_if_capped();
 }
@@ -103,7 +111,10 @@ static void tensor_set(struct ggml_tensor *t, const void *data, size_t offset, s
 #define ggml_backend_graph_compute(b, g) hx::graph_compute((b), (g))
 #define ggml_backend_tensor_get(t, d, o, s) hx::tensor_get((t), (d), (o), (s))
 #define main reference_main
-#include "main.cpp" // resolved through -I/root/reference ; never copied
+#ifndef HX_MAIN
+#define HX_MAIN "main.cpp" // resolved through -I/root/reference ; never copied
+#endif
+#include HX_MAIN // (-DHX_MAIN=... selects the "patched reference" TU of oracle/patch_steps.py)
 #undef main
 #undef ggml_backend_graph_compute
 #undef ggml_backend_tensor_get
@@ -197,6 +208,8 @@ int main(int argc, char **argv) {
     generator.seed(atoi(argv[5]));
     hx::g_outdir = argv[6];
     if (argc > 7) hx::g_max_computes = atoi(argv[7]);
+    if (argc > 8) hx::g_force_len = atoi(argv[8]);
+    hx::g_batch = B;
     mkdir(hx::g_outdir.c_str(), 0755);
     auto tokens = tokenize_like_main(text);
     hx::write_file(hx::g_outdir + "/tokens.i32", tokens.data(), tokens.size() * 4);

@@ -340,7 +340,9 @@ def ddpm_schedule(n_steps: int = 80):
     n0 = 4000
     scale = 1000.0 / n0
     bs, be = scale * 0.0001, scale * 0.02
-    betas = np.array([bs + i * float(F32(be - bs)) / (n0 - 1) for i in range(n0)], dtype=np.float64)
+    # `i * (float)(end - start) / (n - 1)` is evaluated in FLOAT (int * float, float / int) and only then
+    # added to the double start value (main.cpp:5396-5398)
+    betas = np.array([bs + float(F32(F32(i) * F32(be - bs)) / F32(n0 - 1)) for i in range(n0)], dtype=np.float64)
     acp = np.cumprod(1.0 - betas)
     frac = (n0 - 1) / (n_steps - 1)
     tmap = [int(round(i * frac)) if n_steps != 80 else None for i in range(n_steps)]

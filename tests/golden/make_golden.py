@@ -17,6 +17,14 @@ reference's own `cd build && ./tortoise` layout, main.cpp:5078/5625/6046/6551):
     ref_harness hostfn <work>/out_host
     ref_harness sample ... (see below)
     ref_harness tokenize "<sentence>"   for every sentence of CORPUS
+Round-2 additions (`--long`; ~35 minutes of CPU, only these two fixtures are rewritten):
+    ref_harness ar "this is a test message." ../models/mol.bin 1 0 <work>/out_arlong -1 272
+        forced-length run of the UNMODIFIED reference: the harness replaces the stop token's logit by
+        -1e30 in transit for the first 272 read-backs (after dumping the true row), so the KV cache
+        grows past 128 and 256 keys -> ar_long.npz (all fed tokens, logits of ~35 pinned steps)
+    HX_STEPS=200 ref_harness_steps diff <latents of ar_b1.npz> 0 <work>/out_diff200
+        "patched reference" (oracle/patch_steps.py: 80 / 79 literals + table -> run-time step count)
+        -> diffusion200.npz (final mel, 4 teacher-forced passes)
 """
 import argparse
 import glob
@@ -30,6 +38,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
 GOLD = os.path.join(ROOT, "tests", "golden")
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 PROMPT = "this is a test message."
@@ -64,10 +73,67 @@ def i32(p):
     return np.fromfile(p, dtype=np.int32)
 
 
+def make_long(W, build, assemble_only):
+    steps_bin = os.path.join(ROOT, "oracle", "_ref", "ref_harness_steps")
+    lat_path = W + "/lat_b1.f32"
+    np.load(os.path.join(GOLD, "ar_b1.npz"))["trimmed_latents"].astype(np.float32).tofile(lat_path)
+    if not assemble_only:
+        if not os.path.exists(W + "/out_arlong/codes_0.i32"):
+            run([HARNESS, "ar", PROMPT, "../models/mol.bin", "1", "0", W + "/out_arlong", "-1", "272"], build)
+        if not os.path.exists(W + "/out_diff200/mel.f32"):
+            env = dict(os.environ, HX_STEPS="200")
+            print("+ HX_STEPS=200", steps_bin, "diff ...")
+            subprocess.check_call([steps_bin, "diff", lat_path, "0", W + "/out_diff200"], cwd=build, env=env)
+    # ---- forced-length AR run
+    codes = i32(W + "/out_arlong/codes_0.i32")
+    fed = []
+    for c in codes:
+        fed.append(int(c))
+        if c == 8193:
+            break
+    logit_files = sorted(p for p in glob.glob(W + "/out_arlong/ar_get*_c*.f32") if os.path.getsize(p) == 8194 * 4)
+    assert len(logit_files) == len(fed), (len(logit_files), len(fed))  # row k produced sample k
+    T = len(i32(W + "/out_arlong/tokens.i32"))
+    d = {"tokens": i32(W + "/out_arlong/tokens.i32"), "fed_tokens": np.array(fed, np.int32)}
+    # pinned rows: n_keys of row k = T + 2 + k.  Around the 128- and 256-key tile boundaries every
+    # step, plus a sparse sweep (a row is 32 KB)
+    b128, b256 = 128 - T - 2, 256 - T - 2
+    pinned = {0, 1, 2, 40, 80, 100, 140, 180, 220, len(fed) - 2, len(fed) - 1}
+    pinned |= set(range(b128 - 3, b128 + 4)) | set(range(b256 - 3, b256 + 4))
+    for k in sorted(x for x in pinned if 0 <= x < len(logit_files)):
+        d[f"logits_{k}"] = f32(logit_files[k])
+    np.savez(os.path.join(GOLD, "ar_long.npz"), **d)
+    print("ar_long.npz:", len(fed), "fed tokens,", sum(k.startswith("logits_") for k in d), "pinned rows")
+    # ---- 200 sampling steps, patched reference
+    S = f32(W + "/out_diff200/mel.f32").size // 100
+    outs = sorted(glob.glob(W + "/out_diff200/diff_get*_c*.f32"))
+    xs = sorted(glob.glob(W + "/out_diff200/diff_set_noise_tensor_c*.f32"))
+    assert len(outs) == 400 and len(xs) == 400, (len(outs), len(xs))
+    from tortoise_oracle import ddpm_schedule  # noqa: F401  (timestep map cross-check below)
+    frac, cur, tmap = 3999.0 / 199.0, 0.0, []
+    for _ in range(200):
+        tmap.append(int(round(cur)))
+        cur += frac
+    d = {"latents": f32(lat_path), "mel": f32(W + "/out_diff200/mel.f32").reshape(100, S)}
+    for k in (0, 1, 398, 399):
+        d[f"x_{k}"] = f32(xs[k]).reshape(100, S)
+        d[f"out_{k}"] = f32(outs[k]).reshape(200, S)
+        d[f"t_{k}"] = np.array(tmap[199 - k // 2])
+    d["x_2"] = f32(xs[2]).reshape(100, S)  # x after the first sampling step (trajectory check on the CPU)
+    for k in (67, 100, 150):  # mid-trajectory sampler steps: x before, both model outputs, x after
+        d[f"x_{2 * k}"] = f32(xs[2 * k]).reshape(100, S)
+        d[f"out_{2 * k}"] = f32(outs[2 * k]).reshape(200, S)
+        d[f"out_{2 * k + 1}"] = f32(outs[2 * k + 1]).reshape(200, S)
+        d[f"x_{2 * k + 2}"] = f32(xs[2 * k + 2]).reshape(100, S)
+    np.savez(os.path.join(GOLD, "diffusion200.npz"), **d)
+    print("diffusion200.npz: S =", S)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--work", default="/tmp/w")
     ap.add_argument("--assemble", action="store_true")
+    ap.add_argument("--long", action="store_true", help="only the round-2 fixtures (ar_long.npz, diffusion200.npz)")
     a = ap.parse_args()
     W = a.work
     build = os.path.join(W, "build")
@@ -79,6 +145,9 @@ def main():
     for f in ("tokenizer.json", "mol.bin"):
         if not os.path.exists(os.path.join(models, f)):
             shutil.copyfile(os.path.join("/root/reference/models", f), os.path.join(models, f))
+    if a.long:
+        make_long(W, build, a.assemble)
+        return
     if not a.assemble:
         if not os.path.exists(W + "/out_full/audio.f32"):
             run([HARNESS, "full", PROMPT, "../models/mol.bin", "0", W + "/out_full"], build)

@@ -1,0 +1,261 @@
+"""GPU parity of the BENCHMARKED mode (f16 AR weights, `bench.py` dtype f16) and of the configurations
+the round-1 tests did not reach: every decode step against the reference goldens, the per-op f16
+path, > 128 / > 256 cached keys (forced-length reference run), 8 and 16 candidates on one weight
+stream, latents for more than 4 candidates, and the 200-step sampler against the "patched
+reference" (oracle/patch_steps.py).  Everything goes through the C-ABI.
+
+Tolerances.  f32 parity mode keeps the bars of tests/test_ar_gpu.py (logits 2.5e-3, latents 1e-2).
+f16 weights add a weight-rounding term on top of the reference's own fp16 round-trip noise: the
+numpy oracle with f16-rounded weights already sits 2.3e-3 from the reference goldens on the
+synthetic weights (measured on CPU), so the f16 bar on logits is 4e-3 (|logit| <= ~3) and every test
+prints the max-abs it measured; latents / mel / waveform keep the reference's own 1e-2 bar
+(main.cpp:6183-6231).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, nmse
+
+pytestmark = pytest.mark.gpu
+
+F32_LOGIT_TOL = 2.5e-3
+F16_LOGIT_TOL = 4e-3
+LATENT_TOL = 1e-2
+
+
+def _steps(codes500):
+    out = []
+    for c in codes500:
+        out.append(int(c))
+        if c == 8193:
+            break
+    return out
+
+
+@pytest.fixture(scope="module")
+def engine_f16(pkg, model_dir):
+    eng = pkg.Engine(device=0, dtype=pkg.DTYPE_F16, max_batch=16, max_positions=404, parity_quirks=True)
+    eng.load_ar(os.path.join(model_dir, "ggml-model.bin"))
+    eng.load_diffusion(os.path.join(model_dir, "ggml-diffusion-model.bin"))
+    eng.load_vocoder(os.path.join(model_dir, "ggml-vocoder-model.bin"))
+    yield eng
+    eng.close()
+
+
+def _engine(pkg, model_dir, dtype, max_batch, max_positions=404, env=None):
+    env = env or {}
+    for k, v in env.items():
+        os.environ[k] = v
+    try:
+        eng = pkg.Engine(device=0, dtype=dtype, max_batch=max_batch, max_positions=max_positions)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+    eng.load_ar(os.path.join(model_dir, "ggml-model.bin"))
+    return eng
+
+
+# --------------------------------------------------------------------------- (a) f16, every step, B = 1 / 4
+def test_f16_teacher_forced_every_step_b1(engine_f16, golden, voice):
+    g = golden("ar_b1.npz")
+    toks = _steps(g["codes500"])
+    lg = engine_f16.ar_prefill(g["tokens"], voice, 1)
+    errs = [float(np.abs(lg[0] - g["logits_0"]).max())]
+    for i, t in enumerate(toks):
+        lg = engine_f16.ar_step([t], i + 2)
+        if f"logits_{i + 1}" in g.files:
+            errs.append(float(np.abs(lg[0] - g[f"logits_{i + 1}"]).max()))
+    print(f"f16 B=1 teacher-forced logits vs reference: {len(errs)} steps, max-abs {max(errs):.3e} (mean {np.mean(errs):.3e})")
+    assert len(errs) == int(g["n_logit_steps"])
+    assert max(errs) < F16_LOGIT_TOL
+
+
+def test_f16_teacher_forced_b4(engine_f16, golden, voice):
+    g = golden("ar_b4.npz")
+    lg = engine_f16.ar_prefill(g["tokens"], voice, 4)
+    errs = [float(np.abs(lg - g["logits_0"]).max())]
+    seqs = [_steps(g[f"codes500_{b}"]) for b in range(4)]
+    for i in range(max(len(s) for s in seqs)):
+        fed = [seqs[b][i] if i < len(seqs[b]) else 8193 for b in range(4)]
+        live = [b for b in range(4) if i < len(seqs[b])]
+        lg = engine_f16.ar_step(fed, i + 2)
+        if f"logits_{i + 1}" in g.files:
+            errs.append(float(np.abs(lg[live] - g[f"logits_{i + 1}"][live]).max()))
+    print(f"f16 B=4 teacher-forced logits vs reference: {len(errs)} pinned steps, max-abs {max(errs):.3e}")
+    assert len(errs) >= 3 and max(errs) < F16_LOGIT_TOL
+
+
+# --------------------------------------------------------------------------- (b) f16 latents
+def test_f16_latents_b1_and_b4(engine_f16, golden, voice, hostlib_full):
+    g = golden("ar_b1.npz")
+    n = hostlib_full.trim_count(g["codes500"])
+    codes502 = np.concatenate([[8192], g["codes500"], [8193]]).astype(np.int32)[None]
+    lat = engine_f16.ar_latents(g["tokens"], voice, codes502, n_keep=n)
+    e1 = float(np.abs(lat[0, :n] - g["trimmed_latents"].reshape(n, 1024)).max())
+    g4 = golden("ar_b4.npz")
+    codes502 = np.stack([np.concatenate([[8192], g4[f"codes500_{b}"], [8193]]) for b in range(4)]).astype(np.int32)
+    keeps = [hostlib_full.trim_count(g4[f"codes500_{b}"]) for b in range(4)]
+    lat = engine_f16.ar_latents(g4["tokens"], voice, codes502, n_keep=max(keeps))
+    e4 = max(float(np.abs(lat[b, :keeps[b]] - g4[f"trimmed_latents_{b}"].reshape(keeps[b], 1024)).max()) for b in range(4))
+    print(f"f16 latents vs reference: B=1 max-abs {e1:.3e}, B=4 max-abs {e4:.3e}")
+    assert e1 < LATENT_TOL and e4 < LATENT_TOL
+
+
+# --------------------------------------------------------------------------- (c) f16 end to end from the reference's codes
+def test_f16_seed_matched_mel_and_waveform(engine_f16, golden, hostlib_full, voice):
+    g, full = golden("ar_b1.npz"), golden("full_seed0.npz")
+    n = hostlib_full.trim_count(g["codes500"])
+    codes502 = np.concatenate([[8192], g["codes500"], [8193]]).astype(np.int32)[None]
+    lat = engine_f16.ar_latents(g["tokens"], voice, codes502, n_keep=n)[0, :n]
+    rng = hostlib_full.rng(0)
+    for _ in range(2 * int(g["n_logit_steps"])):
+        rng.uniform()
+    mel = hostlib_full.diffusion(engine_f16, rng, lat, 80)
+    ref_mel = full["mel"].reshape(100, -1)
+    audio = hostlib_full.vocoder(engine_f16, rng, mel)
+    ref = full["audio"]
+    print(f"f16 seed-0 mel: max-abs {np.abs(mel - ref_mel).max():.3e} nmse {nmse(mel, ref_mel):.3e}; "
+          f"waveform: max-abs {np.abs(audio - ref).max():.3e} nmse {nmse(audio, ref):.3e}")
+    assert np.abs(mel - ref_mel).max() < 1e-2 or nmse(mel, ref_mel) < 1e-4
+    assert audio.shape == ref.shape and nmse(audio, ref) < 1e-3
+
+
+# --------------------------------------------------------------------------- (d) long context + per-op path vs the reference
+LONG = os.path.join(GOLDEN, "ar_long.npz")
+
+
+def _run_long(eng, g, voice):
+    """teacher-forced replay of the forced-length reference run; returns {step: max-abs error}"""
+    toks = [int(c) for c in g["fed_tokens"]]
+    pinned = sorted(int(k.split("_")[1]) for k in g.files if k.startswith("logits_"))
+    lg = eng.ar_prefill(g["tokens"], voice, 1)
+    errs = {}
+    if 0 in pinned:
+        errs[0] = float(np.abs(lg[0] - g["logits_0"]).max())
+    for i, t in enumerate(toks):
+        if i + 1 > pinned[-1]:
+            break
+        lg = eng.ar_step([t], i + 2)
+        if (i + 1) in pinned:
+            errs[i + 1] = float(np.abs(lg[0] - g[f"logits_{i + 1}"]).max())
+    return errs
+
+
+@pytest.mark.parametrize("mode", ["f32_mega", "f16_mega", "f16_per_op", "f32_per_op"])
+def test_long_context_vs_forced_length_reference(pkg, model_dir, voice, mode):
+    """> 128 and > 256 cached keys against a forced-length run of the UNMODIFIED reference
+    (stop logit suppressed in transit by the harness, tests/golden/make_golden.py --long): the
+    persistent kernels walk several 128-key tiles, the per-op path (TTS_NO_MEGA=1) is pinned here too."""
+    g = np.load(LONG)
+    dtype = pkg.DTYPE_F32 if mode.startswith("f32") else pkg.DTYPE_F16
+    env = {"TTS_NO_MEGA": "1"} if mode.endswith("per_op") else {}
+    eng = _engine(pkg, model_dir, dtype, 1, 404, env)
+    try:
+        errs = _run_long(eng, g, voice)
+    finally:
+        eng.close()
+    n_keys = {s: len(g["tokens"]) + 2 + s for s in errs}
+    assert max(n_keys.values()) > 256 and any(128 < v <= 256 for v in n_keys.values())
+    worst = max(errs, key=errs.get)
+    print(f"{mode}: {len(errs)} pinned steps up to {max(n_keys.values())} keys, max-abs {errs[worst]:.3e} at step {worst}")
+    assert errs[worst] < (F32_LOGIT_TOL if mode.startswith("f32") else F16_LOGIT_TOL)
+
+
+def test_f16_per_op_path_every_step_b1(pkg, model_dir, golden, voice):
+    g = golden("ar_b1.npz")
+    eng = _engine(pkg, model_dir, pkg.DTYPE_F16, 1, 128, {"TTS_NO_MEGA": "1"})
+    try:
+        lg = eng.ar_prefill(g["tokens"], voice, 1)
+        errs = [float(np.abs(lg[0] - g["logits_0"]).max())]
+        for i, t in enumerate(_steps(g["codes500"])):
+            lg = eng.ar_step([t], i + 2)
+            if f"logits_{i + 1}" in g.files:
+                errs.append(float(np.abs(lg[0] - g[f"logits_{i + 1}"]).max()))
+    finally:
+        eng.close()
+    print(f"f16 per-op path vs reference: max-abs {max(errs):.3e}")
+    assert max(errs) < F16_LOGIT_TOL
+
+
+# --------------------------------------------------------------------------- (e) 8 and 16 candidates on one weight stream
+@pytest.mark.parametrize("B", [8, 16, 11])
+def test_f16_batched_decode_vs_oracle(engine_f16, golden, voice, model_dir, B):
+    """One launch per step for up to 16 candidates (ar_mega4.cuh): 4 teacher-forced steps with distinct
+    tokens per candidate against the numpy oracle on f16-rounded weights, and the shared-prefix KV
+    (prefill rows stored once) against per-candidate copies implicitly (the oracle keeps copies)."""
+    import _pkg
+    import tortoise_oracle as O
+    sw = _pkg.import_sub("synth_weights")
+    W = sw.read_container(os.path.join(model_dir, "ggml-model.bin"))
+    g = golden("ar_b1.npz")
+    ar = O.AROracle(W, weight_dtype="f16")
+    ref = ar.prefill(g["tokens"], voice, B)
+    lg = engine_f16.ar_prefill(g["tokens"], voice, B)
+    errs = [float(np.abs(lg - ref).max())]
+    codes = [int(x) for x in g["codes500"][:4]]
+    for i, c in enumerate(codes):
+        toks = np.array([(c + 97 * b) % 8192 for b in range(B)])
+        ref = ar.step(toks, i + 2)
+        lg = engine_f16.ar_step(toks, i + 2)
+        errs.append(float(np.abs(lg - ref).max()))
+    print(f"f16 B={B} vs oracle: max-abs per step {['%.2e' % e for e in errs]}")
+    assert max(errs) < F32_LOGIT_TOL
+
+
+def test_batched_topk_step_is_consistent_with_full_logits(engine_f16, golden, voice):
+    """tts_ar_step_topk: the device-side top-64 (value, index) pairs of every candidate equal the
+    top-64 of the full logits row of the same step (bit-exact values, same index set)."""
+    g = golden("ar_b1.npz")
+    B = 16
+    engine_f16.ar_prefill(g["tokens"], voice, B)
+    toks = [(int(g["codes500"][0]) + 31 * b) % 8192 for b in range(B)]
+    vals, idx = engine_f16.ar_step_topk(toks, 2)
+    full = engine_f16.ar_last_logits()
+    assert vals.shape == (B, 64) and idx.shape == (B, 64)
+    for b in range(B):
+        order = np.argsort(-full[b], kind="stable")[:64]
+        assert set(idx[b].tolist()) == set(order.tolist())
+        assert np.array_equal(np.sort(vals[b])[::-1], full[b][order])
+        assert np.array_equal(full[b][idx[b]], vals[b])
+
+
+@pytest.mark.parametrize("B", [6, 16])
+def test_f16_latents_more_than_four_candidates(engine_f16, golden, voice, model_dir, B):
+    """latent pass for B > 4 (positions ran past the 608-row table): candidates get mel
+    positions 0.. like the reference's B = 4 case; checked against the oracle with the same rule."""
+    import _pkg
+    import tortoise_oracle as O
+    sw = _pkg.import_sub("synth_weights")
+    W = sw.read_container(os.path.join(model_dir, "ggml-model.bin"))
+    g = golden("ar_b1.npz")
+    rs = np.random.RandomState(B)
+    n_keep = 14
+    codes = np.full((B, 502), 83, np.int32)
+    codes[:, 0] = 8192
+    codes[:, 1:1 + n_keep] = rs.randint(0, 8192, size=(B, n_keep))
+    codes[:, -1] = 8193
+    lat = engine_f16.ar_latents(g["tokens"], voice, codes, n_keep=n_keep)
+    ref = O.AROracle(W, weight_dtype="f16").latents(g["tokens"], voice, codes, n_keep=n_keep, parity_quirks=False)
+    err = float(np.abs(lat[:, :n_keep] - ref).max())
+    print(f"f16 latents B={B} vs oracle: max-abs {err:.3e}")
+    assert np.isfinite(lat).all() and err < LATENT_TOL
+
+
+# --------------------------------------------------------------------------- (f) 200 sampling steps vs the patched reference
+def test_diffusion_200_steps_vs_patched_reference(engine_f32, hostlib_full):
+    """--steps 200 (BASELINE configs[3]): schedule + respacing + sampler against the reference built with its
+    80 / 79 literals replaced by a run-time step count (oracle/patch_steps.py, "patched reference")."""
+    g = np.load(os.path.join(GOLDEN, "diffusion200.npz"))
+    lat = g["latents"].reshape(-1, 1024)
+    rng = hostlib_full.rng(0)
+    mel = hostlib_full.diffusion(engine_f32, rng, lat, 200)
+    ref = g["mel"]
+    print(f"200-step mel vs patched reference: max-abs {np.abs(mel - ref).max():.3e} nmse {nmse(mel, ref):.3e}")
+    assert mel.shape == ref.shape
+    assert np.abs(mel - ref).max() < 1e-2 or nmse(mel, ref) < 1e-4
+    # teacher-forced passes late in the trajectory (timestep map entries only a 200-step run has)
+    for k in (0, 1, 398, 399):
+        out = engine_f32.diffusion_eps(lat, g[f"x_{k}"], int(g[f"t_{k}"]), conditioning_free=bool(k % 2))
+        assert nmse(out, g[f"out_{k}"]) < 1e-5, k

@@ -197,3 +197,44 @@ def test_text_front_end_normalize_and_split(hl):
     assert hl.split_text("short", 100) == ["short"]
     assert hl.split_text("", 100) == []
     assert hl.split_text("a" * 50, 16) == ["a" * 16, "a" * 16, "a" * 16, "aa"]
+
+
+def test_sparse_sampler_matches_full_row_sampler_bit_exactly(hl):
+    """tts_host_sample_sparse (fed with the 64 largest raw logits, as tts_ar_step_topk delivers them) draws
+    the same tokens from the same generator state as the full-row sampler -- itself pinned against the
+    reference's process_logits_and_sample above -- or declines without touching the generator."""
+    g = np.load(os.path.join(GOLDEN, "sampler.npz"))
+    rs = np.random.RandomState(3)
+    n_sparse = n_decl = 0
+    for tag in ("a", "b"):
+        logits = g[f"{tag}_logits"]
+        for trial in range(40):
+            b = trial % 4
+            row = logits[b].copy()
+            if trial >= 8:  # perturbed copies: different winners, penalised tokens inside / outside the set
+                row = (row + rs.normal(0, 0.3, size=row.shape)).astype(np.float32)
+            order = np.argsort(-row, kind="stable")[:64]
+            prev = np.array([int(order[rs.randint(0, 64)]), int(rs.randint(0, 8194))] if trial % 3 else [1] * 17 + [8192],
+                            np.int32)
+            seed = 100 + trial
+            r_full, r_sp = hl.rng(seed), hl.rng(seed)
+            want, want_lp = hl.sample(r_full, row[None], prev[None], want_logprob=True)
+            perm = rs.permutation(64)  # the device emits the pairs unsorted
+            got = hl.sample_sparse(r_sp, row[order][perm], order[perm], prev)
+            if got is None:
+                n_decl += 1
+                assert r_sp.uniform() == hl.rng(seed).uniform()  # generator untouched
+                continue
+            n_sparse += 1
+            assert got[0] == int(want[0]), (tag, trial)
+            assert got[1] == float(want_lp[0]) or (np.isnan(got[1]) and np.isnan(want_lp[0]))
+            assert r_sp.uniform() == r_full.uniform()  # same number of draws consumed
+    assert n_sparse >= 60, (n_sparse, n_decl)
+
+
+def test_sparse_sampler_declines_when_the_cut_is_too_close(hl):
+    """near-uniform row: the 64th largest value sits inside the survivor window of the 50th -> decline"""
+    row = np.zeros(8194, np.float32)
+    row[:70] = 1.0
+    order = np.argsort(-row, kind="stable")[:64]
+    assert hl.sample_sparse(hl.rng(0), row[order], order, np.array([5], np.int32)) is None

@@ -78,6 +78,43 @@ def test_ddpm_step_oracle_reproduces_reference_trajectory():
         assert int(hs[i, 8]) == k["timestep"]
 
 
+def test_200_step_schedule_against_patched_reference():
+    """--steps 200 (BASELINE configs[3]): first and last sampling step of the "patched reference"
+    (oracle/patch_steps.py: the 80 / 79 literals become a run-time step count) reproduced from its own
+    model outputs -- pins the 200-entry timestep map, the respaced betas and both ends of the schedule
+    for the oracle AND the C++ host code."""
+    import _pkg
+    import tortoise_oracle as O
+    g = np.load(os.path.join(GOLDEN, "diffusion200.npz"))
+    S = g["x_0"].shape[1]
+    hl = _pkg.import_sub("host").HostLib()
+    noise = hl.rng(0).normal(2 * 100 * S).reshape(2, 100, S)
+    assert np.array_equal(noise[0], g["x_0"])
+    sched = O.ddpm_schedule(200)
+    x1 = O.ddpm_step(g["x_0"], g["out_0"], g["out_1"], noise[1], sched[0])
+    assert np.abs(x1 - g["x_2"]).max() < 2e-6
+    assert sched[199]["last"] and sched[199]["timestep"] == 0
+    mel = O.ddpm_step(g["x_398"], g["out_398"], g["out_399"], np.zeros_like(g["x_0"]), sched[199])
+    assert np.abs(mel - g["mel"]).max() < 2e-6
+    hs = hl.ddpm_schedule(200)
+    tmap = hl.timestep_map(200)
+    for i, k in enumerate(sched):
+        row = [k["cfk"], k["sqrt_recip"], k["sqrt_recipm1"], k["coef1"], k["coef2"], k["min_log"], k["max_log"]]
+        assert np.allclose(hs[i, :7], np.array(row, dtype=np.float32), rtol=1e-6, atol=0), i
+        assert int(hs[i, 8]) == k["timestep"] == int(tmap[199 - i])
+    assert int(g["t_0"]) == int(tmap[199]) and int(g["t_398"]) == int(tmap[0])
+    # mid-trajectory sampler steps: the C++ host schedule (the PRODUCT code) reproduces the patched
+    # reference's x bit for bit; the numpy oracle to float rounding
+    names = ["cfk", "sqrt_recip", "sqrt_recipm1", "coef1", "coef2", "min_log", "max_log"]
+    for k in (67, 100, 150):
+        noise = hl.rng(0).normal((k + 2) * 100 * S).reshape(k + 2, 100, S)[k + 1]
+        args = (g[f"x_{2 * k}"], g[f"out_{2 * k}"], g[f"out_{2 * k + 1}"], noise)
+        assert np.abs(O.ddpm_step(*args, sched[k]) - g[f"x_{2 * k + 2}"]).max() < 2e-6
+        hk = dict(sched[k])
+        hk.update({n: np.float32(hs[k, j]) for j, n in enumerate(names)})
+        assert np.array_equal(O.ddpm_step(*args, hk), g[f"x_{2 * k + 2}"]), k
+
+
 def test_vocoder_oracle(weights):
     import tortoise_oracle as O
     g = np.load(os.path.join(GOLDEN, "vocoder.npz"))

@@ -89,6 +89,15 @@ def test_b4_free_running_prefix(engine_f32, golden, hostlib_full, voice):
             assert np.abs(lat[b, :n] - g[f"trimmed_latents_{b}"].reshape(n, 1024)).max() < 1e-2
     # the first sampled code of every candidate comes from bit-identical prefill rows
     assert all(codes[b][0] == g[f"codes500_{b}"][0] for b in range(4))
+    # free-running parity: measured on B200 all four candidates are token-identical to the reference; a single
+    # candidate may flip on a near-tie (0.4 % per step), two or more flips mean a real defect
+    pref = []
+    for b in range(4):
+        want = _first_stop(g[f"codes500_{b}"])
+        mine = _first_stop(codes[b])
+        pref.append(next((i for i, (x, y) in enumerate(zip(mine, want)) if x != y), len(want)) / len(want))
+    print("identical prefix fraction per candidate:", pref)
+    assert sum(same) >= 3 and min(pref) > 0.2
 
 
 def test_cli_binary_end_to_end_seed0(model_dir, golden, tmp_path, pkg):
@@ -108,10 +117,18 @@ def test_cli_binary_end_to_end_seed0(model_dir, golden, tmp_path, pkg):
     audio = np.frombuffer(raw[44:], dtype=np.float32)
     assert struct.unpack("<I", raw[40:44])[0] == audio.size * 4 and struct.unpack("<I", raw[4:8])[0] == 36 + audio.size * 4
     assert (audio.size + 6) % 256 == 0 and np.isfinite(audio).all()
+    import json
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    mine, want = info["codes"], _first_stop(golden("ar_b1.npz")["codes500"])
+    m = next((i for i, (a, b) in enumerate(zip(mine, want)) if a != b), min(len(mine), len(want)))
+    print(f"CLI seed-0 codes: identical prefix {m} of {len(want)} reference codes")
+    # the free-running run follows the reference until the first legitimate flip (DESIGN.md "parity floor":
+    # 0.4 % per step under the reference's own fp16 noise; measured on B200: the first 6 codes agree)
+    assert m >= 5, (mine, want)
+    assert audio.size == ((len(mine) + 8) * 4 * 24000 // 22050 + 10) * 256 - 6  # S = L*4*24000/22050 frames, L = codes + 8
     ref = golden("full_seed0.npz")["audio"]
-    if audio.size == ref.size:
-        print(f"CLI seed-0 waveform vs reference: nmse {nmse(audio, ref):.3e}")
-    print(r.stdout.strip().splitlines()[-1])
+    if mine == want:  # same codes -> seed-matched waveform parity through the binary
+        assert audio.size == ref.size and nmse(audio, ref) < 1e-3
 
 
 def test_forced_length_bench_mode(engine_f32, golden, hostlib_full, voice):

@@ -70,6 +70,8 @@ def load_library() -> C.CDLL:
     lib.tts_ar_prefill.argtypes = [vp, i32p, i32, f32p, i32, f32p]
     lib.tts_ar_step.argtypes = [vp, i32p, i32, f32p]
     lib.tts_ar_step_dev.argtypes = [vp, i32p, i32, P(vp)]
+    lib.tts_ar_step_topk.argtypes = [vp, i32p, i32, f32p, i32p, i32p]
+    lib.tts_ar_logits.argtypes = [vp, f32p]
     lib.tts_ar_latents.argtypes = [vp, i32p, i32, f32p, i32p, i32, i32, f32p]
     lib.tts_diffusion_eps.argtypes = [vp, f32p, i32, f32p, i32, i32, i32, f32p]
     lib.tts_diffusion_sample.argtypes = [vp, f32p, i32, i32, i32, f32p, f32p]
@@ -150,6 +152,22 @@ class Engine:
         tokens, tp = _i32(tokens)
         out = np.empty((self.B, MEL_VOCAB), dtype=np.float32)
         self._chk(self.lib.tts_ar_step(self.h, tp, pos_id, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def ar_step_topk(self, tokens, pos_id):
+        """(values [B][64], indices [B][64]) of the device-side top-k pre-selection; raises if a row overflowed"""
+        tokens, tp = _i32(tokens)
+        vals = np.empty((self.B, 64), dtype=np.float32)
+        idx = np.empty((self.B, 64), dtype=np.int32)
+        flags = np.empty(self.B, dtype=np.int32)
+        self._chk(self.lib.tts_ar_step_topk(self.h, tp, pos_id, vals.ctypes.data_as(C.POINTER(C.c_float)),
+                                            idx.ctypes.data_as(C.POINTER(C.c_int32)), flags.ctypes.data_as(C.POINTER(C.c_int32))))
+        self.topk_flags = flags
+        return vals, idx
+
+    def ar_last_logits(self):
+        out = np.empty((self.B, MEL_VOCAB), dtype=np.float32)
+        self._chk(self.lib.tts_ar_logits(self.h, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
     def ar_step_dev(self, tokens, pos_id):

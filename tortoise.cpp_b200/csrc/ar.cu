@@ -10,6 +10,7 @@
 #include "wsgemv.cuh"
 #include "ar_mega2.cuh"
 #include "ar_mega3.cuh"
+#include "ar_mega4.cuh"
 
 namespace tts {
 
@@ -151,6 +152,22 @@ void ar_load(tts_ctx *c, const char *path) {
       }
       m.mega_epoch = 0;
     }
+    if (B > 4 && m.dtype == TTS_DTYPE_F16) {  // 5..16 candidates on one weight stream (ar_mega4.cuh)
+      const size_t sizes[5] = {size_t(2) * 16 * kDim, size_t(2) * 16 * kDim, size_t(16) * 3072, size_t(2) * 16 * (kFF / 2),
+                               size_t(2) * 16 * kHeads * M4_REC};
+      uint2 **ptrs[5] = {&m.l4_h, &m.l4_h2, &m.l4_qkv, &m.l4_m, &m.l4_att};
+      for (int i = 0; i < 5; ++i) {
+        m.l4_bytes[i] = sizes[i] * sizeof(uint2);
+        TTS_CUDA_TRY(ctx_malloc(c, ptrs[i], m.l4_bytes[i]));
+        TTS_CUDA_TRY(cudaMemset(*ptrs[i], 0, m.l4_bytes[i]));
+      }
+    }
+    TTS_CUDA_TRY(ctx_malloc(c, &s.d_topv, B * AR_TOPK * 4));
+    TTS_CUDA_TRY(ctx_malloc(c, &s.d_topi, B * AR_TOPK * 4));
+    TTS_CUDA_TRY(ctx_malloc(c, &s.d_topf, B * 4));
+    TTS_CUDA_TRY(ctx_malloc_host(c, &s.h_topv, B * AR_TOPK * 4));
+    TTS_CUDA_TRY(ctx_malloc_host(c, &s.h_topi, B * AR_TOPK * 4));
+    TTS_CUDA_TRY(ctx_malloc_host(c, &s.h_topf, B * 4));
     const char *tr = getenv("TTS_MEGA_TRACE");
     if (tr && (tr[0] == '1' || tr[0] == '2')) {
       m.mega_dbg_mode = tr[0] - '0';
@@ -305,6 +322,45 @@ static void launch_mega2_t(tts_ctx *c, int B, int n_past, int pos_id) {
   }
 }
 
+// 5..16 candidates: ONE launch, one weight stream (ar_mega4.cuh; f16 weights)
+template <int BT>
+static void launch_mega4_bt(tts_ctx *c, Mega4Args &a) {
+  auto k = ar_decode_mega4_kernel<BT>;
+  const size_t smem = mega4_smem_bytes<BT>();
+  ensure_smem_attr(k, smem);
+  void *args[] = {&a};
+  TTS_CUDA_TRY(cudaLaunchCooperativeKernel((void *)k, dim3(c->num_sms), dim3(M2_THREADS), args, smem, c->stream));
+  c->launches += 1;
+}
+static void launch_mega4(tts_ctx *c, int B, int n_past, int pos_id) {
+  ArModel &m = c->ar;
+  ArState &s = c->ars;
+  if (m.mega_epoch >= (1u << 24) - 64) {
+    uint2 *ptrs[5] = {m.l4_h, m.l4_h2, m.l4_qkv, m.l4_m, m.l4_att};
+    for (int i = 0; i < 5; ++i) TTS_CUDA_TRY(cudaMemsetAsync(ptrs[i], 0, m.l4_bytes[i], c->stream));
+    uint2 *p2[5] = {m.ll_h, m.ll_h2, m.ll_qkv, m.ll_m, m.ll_att};
+    for (int i = 0; i < 5; ++i) TTS_CUDA_TRY(cudaMemsetAsync(p2[i], 0, m.ll_bytes[i], c->stream));
+    m.mega_epoch = 0;
+  }
+  Mega4Args a{};
+  a.layers = (const MegaLayer *)m.mega_layers;
+  a.lnf_w = m.lnf_w; a.lnf_b = m.lnf_b; a.lm0_w = m.lm0_w; a.lm0_b = m.lm0_b; a.lm_b = m.lm_b; a.lm_w = m.lm_w;
+  a.mel_emb = m.mel_emb; a.mel_pos = m.mel_pos; a.tokens = s.d_tokens;
+  a.ll_h = m.l4_h; a.ll_h2 = m.l4_h2; a.ll_qkv = m.l4_qkv; a.ll_m = m.l4_m; a.ll_att = m.l4_att;
+  a.logits = s.logits; a.kc = s.kc; a.vc = s.vc;
+  a.B = B; a.Bmax = s.Bmax; a.P = s.P; a.n_past = n_past; a.pos_id = pos_id;
+  a.n_prefix = s.n_prefix;
+  a.epoch = ++m.mega_epoch;
+  a.nrep = 2;
+  if (B <= 8) launch_mega4_bt<8>(c, a);
+  else launch_mega4_bt<16>(c, a);
+}
+
+// which decode path serves B candidates: the shared-prefix single-launch kernel needs f16 weights
+static bool use_mega4(const tts_ctx *c, int B) {
+  return c->use_mega && c->ar.dtype == TTS_DTYPE_F16 && B > 4 && B <= 16 && c->ars.P <= 1024 && c->ar.l4_h != nullptr;
+}
+
 static void ensure_rows(tts_ctx *c, size_t rows) {
   ArState &s = c->ars;
   if (rows <= s.rows_cap) return;
@@ -376,7 +432,9 @@ void ar_prefill(tts_ctx *c, const int32_t *text, int T, const float *voice, int 
   L(ar_embed_rows_kernel, dim3(R, 1), dim3(256), 0, (const int *)s.d_text, T, (const float *)s.d_voice,
     (const int *)s.d_tokens, (const int *)s.d_state, 1, (const float *)m.text_emb, (const float *)m.text_pos,
     (const float *)m.mel_emb, (const float *)m.mel_pos, s.H);
-  enqueue_rows_layers(c, L, 1, R, B);
+  // 5..16 candidates on the single-launch path: the prompt's K/V rows are stored once (slot 0)
+  const bool shared = use_mega4(c, B);
+  enqueue_rows_layers(c, L, 1, R, shared ? 1 : B);
   L(bcast_row_kernel, dim3(B), dim3(256), 0, (const float *)(s.H + size_t(R - 1) * kDim), s.h, kDim);
   enqueue_lm_head(c, L, B);
   if (logits_out)
@@ -389,6 +447,7 @@ void ar_prefill(tts_ctx *c, const int32_t *text, int T, const float *voice, int 
   s.B = B;
   s.T = T;
   s.n_past = R;
+  s.n_prefix = shared ? R : 0;
 }
 
 static void build_step_graph(tts_ctx *c, int B) {
@@ -428,6 +487,7 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
   // the pinned token / state words are read by copies queued on the stream (captured in the per-op
   // graph): a back-to-back asynchronous step must not overwrite them before the previous one ran
   const bool mega = c->use_mega && s.P <= 1024;
+  if (s.n_prefix > 0 && !mega) throw ArgError("internal: shared-prefix KV needs the persistent decode kernel");
   if (!sync_out && !mega) TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   for (int b = 0; b < B; ++b) s.h_tokens[b] = tokens[b];
   s.h_state[0] = s.n_past;
@@ -442,9 +502,11 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
       TTS_CUDA_TRY(cudaGetLastError());
       c->launches += 1;
     }
-    if (c->ar.dtype == TTS_DTYPE_F16) launch_mega2_t<__half>(c, B, s.n_past, pos_id);
+    if (s.n_prefix > 0) launch_mega4(c, B, s.n_past, pos_id);
+    else if (c->ar.dtype == TTS_DTYPE_F16) launch_mega2_t<__half>(c, B, s.n_past, pos_id);
     else launch_mega2_t<float>(c, B, s.n_past, pos_id);
-    TTS_CUDA_TRY(cudaMemcpyAsync(s.h_logits, s.logits, size_t(B) * kMelVocab * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (logits_out)
+      TTS_CUDA_TRY(cudaMemcpyAsync(s.h_logits, s.logits, size_t(B) * kMelVocab * 4, cudaMemcpyDeviceToHost, c->stream));
   } else if (c->use_graph) {
     if (!s.step_graph || s.step_graph_B != B) build_step_graph(c, B);
     TTS_CUDA_TRY(cudaGraphLaunch(s.step_graph, c->stream));
@@ -477,6 +539,36 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
       }
     }
   }
+}
+
+// One decode step whose result crosses PCIe as AR_TOPK (value, index) pairs per candidate instead of
+// 8194 floats (reference D2H: main.cpp:4767).  flags_out[b] != 0: ties overflowed, fetch the row.
+void ar_step_topk(tts_ctx *c, const int32_t *tokens, int pos_id, float *vals_out, int32_t *idx_out, int32_t *flags_out) {
+  ArState &s = c->ars;
+  ar_step(c, tokens, pos_id, nullptr, false);
+  const int B = s.B;
+  ar_topk_kernel<<<B, 256, 0, c->stream>>>(s.logits, s.d_topv, s.d_topi, s.d_topf);
+  TTS_CUDA_TRY(cudaGetLastError());
+  c->launches += 1;
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.h_topv, s.d_topv, size_t(B) * AR_TOPK * 4, cudaMemcpyDeviceToHost, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.h_topi, s.d_topi, size_t(B) * AR_TOPK * 4, cudaMemcpyDeviceToHost, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.h_topf, s.d_topf, size_t(B) * 4, cudaMemcpyDeviceToHost, c->stream));
+  TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  c->total_ms += c->last_ms;
+  memcpy(vals_out, s.h_topv, size_t(B) * AR_TOPK * 4);
+  memcpy(idx_out, s.h_topi, size_t(B) * AR_TOPK * 4);
+  memcpy(flags_out, s.h_topf, size_t(B) * 4);
+}
+
+// full logits [B][8194] of the last prefill / step (fallback of the top-k path, tests)
+void ar_logits(tts_ctx *c, float *logits_out) {
+  ArState &s = c->ars;
+  if (!c->ar.loaded || s.B == 0) throw ArgError("tts_ar_logits before tts_ar_prefill");
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.h_logits, s.logits, size_t(s.B) * kMelVocab * 4, cudaMemcpyDeviceToHost, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  memcpy(logits_out, s.h_logits, size_t(s.B) * kMelVocab * 4);
 }
 
 // Latent pass.  Reference quirk A-4: the mel position table is only written for
@@ -577,7 +669,9 @@ void ar_bench_step(tts_ctx *c, int iters, float *ms, double *bytes) {
   *ms = timed > 0 ? t / timed : 0.f;
   const double n_mean = n0 + 1 + 0.5 * iters;
   const double B = s.B;
-  *bytes = double(c->ar.decode_weight_bytes) + 2.0 * kLayers * kDim * B * (n_mean + 1) * 2.0 /*KV read, f16*/ +
+  // (shared-prefix KV, SURVEY 8d: the prompt rows are read once per step, not once per candidate)
+  const double kv_rows = s.n_prefix > 0 ? s.n_prefix + B * (n_mean + 1 - s.n_prefix) : B * (n_mean + 1);
+  *bytes = double(c->ar.decode_weight_bytes) + 2.0 * kLayers * kDim * kv_rows * 2.0 /*KV read, f16*/ +
            2.0 * kLayers * kDim * B * 2.0 /*KV append*/ + (B + 1) * kDim * 4.0 /*embedding rows*/ +
            double(kMelVocab) * B * 4.0 /*logits*/;
 }

@@ -338,6 +338,86 @@ static __global__ void convert_kernel(const float *src, WT *dst, size_t n) {
   }
 }
 
+// Device-side top-k pre-selection of a logits row (the reference copies all 8194
+// floats per candidate to the host every step, main.cpp:4767).  One CTA per candidate: radix select
+// (4 x 8 bits over order-preserving keys) of the TOPK-th largest value, then every larger entry plus
+// the lowest-index ties are emitted as (value, index) pairs -- unsorted; the host sampler orders
+// them itself.  flags[b] = 1 when more than 256 entries tie at the threshold (the host then fetches
+// the full row).  The host-side sampler proves that TOPK = 64 entries reproduce the reference's
+// repetition penalty + top-k 50 + top-p + multinomial bit-exactly, or asks for the full row.
+constexpr int AR_TOPK = 64;
+static __global__ void __launch_bounds__(256) ar_topk_kernel(const float *logits, float *vals, int *idx, int *flags) {
+  __shared__ uint32_t keys[kMelVocab];
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_remaining, s_cnt, s_ntie;
+  __shared__ int s_ties[256];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float *row = logits + size_t(b) * kMelVocab;
+  for (int i = t; i < kMelVocab; i += 256) {
+    const uint32_t u = __float_as_uint(row[i]);
+    keys[i] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // unsigned order == float order
+  }
+  if (t == 0) { s_cnt = 0; s_ntie = 0; }
+  uint32_t prefix = 0;
+  unsigned int remaining = AR_TOPK;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[t] = 0;
+    __syncthreads();
+    const uint32_t mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = t; i < kMelVocab; i += 256) {
+      const uint32_t k = keys[i];
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned int rem = remaining;
+      int bin = 255;
+      for (; bin > 0; --bin) {
+        const unsigned int c = hist[bin];
+        if (c >= rem) break;
+        rem -= c;
+      }
+      s_prefix = prefix | (uint32_t(bin) << shift);
+      s_remaining = rem;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    remaining = s_remaining;
+    __syncthreads();
+  }
+  // prefix = key of the TOPK-th largest entry; `remaining` of the entries equal to it belong to the set
+  for (int i = t; i < kMelVocab; i += 256) {
+    const uint32_t k = keys[i];
+    if (k > prefix) {
+      const unsigned int pos = atomicAdd(&s_cnt, 1u);
+      vals[b * AR_TOPK + pos] = row[i];
+      idx[b * AR_TOPK + pos] = i;
+    } else if (k == prefix) {
+      const unsigned int pos = atomicAdd(&s_ntie, 1u);
+      if (pos < 256u) s_ties[pos] = i;
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    const unsigned int ng = s_cnt, nt = s_ntie;
+    int overflow = nt > 256u ? 1 : 0;
+    if (!overflow) {
+      for (unsigned int i = 1; i < nt; ++i) {  // ascending indices (almost always a single entry)
+        const int v = s_ties[i];
+        int j = int(i) - 1;
+        for (; j >= 0 && s_ties[j] > v; --j) s_ties[j + 1] = s_ties[j];
+        s_ties[j + 1] = v;
+      }
+      for (unsigned int i = 0; i < remaining && ng + i < AR_TOPK; ++i) {
+        vals[b * AR_TOPK + ng + i] = row[s_ties[i]];
+        idx[b * AR_TOPK + ng + i] = s_ties[i];
+      }
+    }
+    flags[b] = overflow;
+  }
+}
+
 // tokens of one decode step, passed by value (max_batch <= 64)
 struct TokenArgs {
   int tok[64];

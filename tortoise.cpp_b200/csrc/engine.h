@@ -54,16 +54,22 @@ struct ArModel {
   uint2 *ll_h = nullptr, *ll_h2 = nullptr, *ll_qkv = nullptr, *ll_m = nullptr, *ll_att = nullptr;
   size_t ll_bytes[5] = {0, 0, 0, 0, 0};
   unsigned int mega_epoch = 0;  // launch counter = tag generation
+  // exchange buffers of the 5..16-candidate step (ar_mega4.cuh), laid out for 16 candidates
+  uint2 *l4_h = nullptr, *l4_h2 = nullptr, *l4_qkv = nullptr, *l4_m = nullptr, *l4_att = nullptr;
+  size_t l4_bytes[5] = {0, 0, 0, 0, 0};
 };
 
 struct ArState {
   int Bmax = 0, P = 0;
   int B = 0, T = 0, n_past = 0;
+  int n_prefix = 0;  // > 0: the prompt's K/V rows are stored once, in candidate slot 0 (ar_mega4.cuh)
   float *h = nullptr, *q = nullptr, *attn = nullptr, *m = nullptr, *logits = nullptr;
   __half *kc = nullptr, *vc = nullptr;  // [30][Bmax][16][P][64]
   int *d_tokens = nullptr, *d_state = nullptr;
   int *h_tokens = nullptr, *h_state = nullptr;  // pinned
   float *h_logits = nullptr;                    // pinned
+  float *d_topv = nullptr, *h_topv = nullptr;   // device top-k (value, index) pairs + overflow flags, and their pinned mirror
+  int *d_topi = nullptr, *h_topi = nullptr, *d_topf = nullptr, *h_topf = nullptr;
   // row buffers for prefill / latent pass (grown on demand)
   size_t rows_cap = 0;
   float *H = nullptr, *QKV = nullptr, *Z = nullptr;
@@ -144,6 +150,8 @@ inline void ctx_free_all(tts_ctx *c) {
 void ar_load(tts_ctx *c, const char *path);
 void ar_prefill(tts_ctx *c, const int32_t *text, int T, const float *voice, int B, float *logits_out);
 void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, bool sync_out);
+void ar_step_topk(tts_ctx *c, const int32_t *tokens, int pos_id, float *vals_out, int32_t *idx_out, int32_t *flags_out);
+void ar_logits(tts_ctx *c, float *logits_out);
 void ar_latents(tts_ctx *c, const int32_t *text, int T, const float *voice, const int32_t *codes, int B,
                 int n_keep, float *out);
 void ar_bench_gemv(tts_ctx *c, int op, int B, int iters, float *ms, double *bytes);

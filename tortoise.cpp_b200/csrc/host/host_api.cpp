@@ -13,6 +13,7 @@ namespace tts_host {
 bool scrape_vocab(const std::string &path, std::map<std::string, int32_t> &vocab);
 std::vector<int32_t> tokenize_message(const std::map<std::string, int32_t> &vocab, std::string message, bool warn);
 int sample_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev, float *logprob);
+int sample_sparse_one(Rng &r, const float *vals, const int32_t *idx, int n, const int32_t *prev, int n_prev, float *logprob);
 int sample_literal_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev);
 void apply_padding(std::vector<int32_t> &vec);
 int trim_count(const int32_t *codes500);
@@ -50,6 +51,16 @@ int tts_host_sample(tts_rng *r, const float *logits, const int32_t *prev, int n_
   for (int b = 0; b < B; ++b)
     out[b] = tts_host::sample_one(r->r, logits + size_t(b) * 8194, prev + size_t(b) * n_prev, n_prev,
                                   logprob ? logprob + b : nullptr);
+  return 0;
+}
+int tts_host_sample_sparse(tts_rng *r, const float *vals, const int32_t *idx, int n, const int32_t *prev, int n_prev,
+                           int32_t *sample_out, float *logprob) {
+  if (!r || !vals || !idx || !prev || !sample_out) return -1;
+  for (int i = 0; i < n_prev; ++i)
+    if (prev[i] < 0 || prev[i] >= 8194) return -1;
+  const int s = tts_host::sample_sparse_one(r->r, vals, idx, n, prev, n_prev, logprob);
+  if (s < 0) return 1;  // the full row is needed (nothing was drawn from the generator)
+  *sample_out = s;
   return 0;
 }
 int tts_host_sample_reference_order(tts_rng *r, const float *logits, const int32_t *prev, int n_prev, int B,

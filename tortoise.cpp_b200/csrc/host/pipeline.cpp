@@ -12,6 +12,7 @@
 
 namespace tts_host {
 int sample_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev, float *logprob);
+int sample_sparse_one(Rng &r, const float *vals, const int32_t *idx, int n, const int32_t *prev, int n_prev, float *logprob);
 void apply_padding(std::vector<int32_t> &vec);
 int trim_count(const int32_t *codes500);
 }  // namespace tts_host
@@ -37,13 +38,41 @@ int tts_host_autoregressive(struct tts_ctx *ctx, tts_rng *rng, const int32_t *to
   std::vector<double> lp_sum(B, 0.0);
   std::vector<int> lp_n(B, 0);
   std::vector<char> done(B, 0);
+  // device-side pre-selection (steps after the prefill): TTS_AR_TOPK (value, index) pairs per candidate
+  // cross PCIe instead of 8194 floats; the full row is fetched only when the sparse sampler asks for it
+  std::vector<float> top_v(size_t(B) * TTS_AR_TOPK);
+  std::vector<int32_t> top_i(size_t(B) * TTS_AR_TOPK), top_f(B, 0);
+  bool sparse = false, have_full = true;
   int i = 0;
   for (;;) {
     for (int b = 0; b < B; ++b) {
-      float *row = logits.data() + size_t(b) * V;
-      if (opt.forced_codes > 0 && i < opt.forced_codes) row[STOP] = -1e30f;  // bench mode: no early stop
       float lp = 0.f;
-      samples[b] = tts_host::sample_one(rng->r, row, prev.data() + size_t(b) * n_prev, n_prev, &lp);
+      int smp = -1;
+      const bool suppress_stop = opt.forced_codes > 0 && i < opt.forced_codes;  // bench mode: no early stop
+      if (sparse && !top_f[b]) {
+        // (a suppressed stop token leaves the set: what remains are the largest entries of the modified row)
+        float tv[TTS_AR_TOPK];
+        int32_t ti[TTS_AR_TOPK];
+        int n = 0;
+        for (int k = 0; k < TTS_AR_TOPK; ++k) {
+          const int32_t id = top_i[size_t(b) * TTS_AR_TOPK + k];
+          if (suppress_stop && id == STOP) continue;
+          tv[n] = top_v[size_t(b) * TTS_AR_TOPK + k];
+          ti[n++] = id;
+        }
+        smp = tts_host::sample_sparse_one(rng->r, tv, ti, n, prev.data() + size_t(b) * n_prev, n_prev, &lp);
+      }
+      if (smp < 0) {
+        if (!have_full) {
+          rc = tts_ar_logits(ctx, logits.data());
+          if (rc != TTS_OK) return rc;
+          have_full = true;
+        }
+        float *row = logits.data() + size_t(b) * V;
+        if (suppress_stop) row[STOP] = -1e30f;
+        smp = tts_host::sample_one(rng->r, row, prev.data() + size_t(b) * n_prev, n_prev, &lp);
+      }
+      samples[b] = smp;
       if (opt.forced_codes > 0 && i >= opt.forced_codes) samples[b] = STOP;
       if (!done[b] && std::isfinite(lp)) {
         lp_sum[b] += lp;
@@ -69,7 +98,13 @@ int tts_host_autoregressive(struct tts_ctx *ctx, tts_rng *rng, const int32_t *to
     for (int b = 0; b < B; ++b)
       if (seqs[b].size() > 500) return TTS_ELIMIT;  // apply_padding asserts <= 500 (main.cpp:4517)
     if (opt.max_steps > 0 && i + 1 >= opt.max_steps) return TTS_ELIMIT;
-    rc = tts_ar_step(ctx, samples.data(), i + 2, logits.data());  // fixed_position = i + 2 (main.cpp:5227)
+    if (opt.full_logits) {
+      rc = tts_ar_step(ctx, samples.data(), i + 2, logits.data());  // fixed_position = i + 2 (main.cpp:5227)
+    } else {
+      rc = tts_ar_step_topk(ctx, samples.data(), i + 2, top_v.data(), top_i.data(), top_f.data());
+      sparse = true;
+      have_full = false;
+    }
     if (rc != TTS_OK) return rc;
     i += 1;
   }

@@ -97,39 +97,15 @@ static float kth_largest_50(const float *x) {
   return heap[0];
 }
 
-// returns -1 when it must defer to the literal path (ties among survivors)
-//
-// Cost matters: the sampler sits between two decode steps (a step is ~0.45 ms on B200, and 16
-// candidates are sampled one after the other).  The 50th-largest value is found with a 50-entry
-// min-heap in ONE pass over the penalised raw logits (division by the temperature is monotone,
-// so it is applied to the handful of candidates around the threshold only; the survivor test
-// itself is done on the divided values exactly as the reference does it).
-static int sample_fast_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev, float *logprob) {
-  thread_local std::vector<float> lg;
-  lg.assign(logits_row, logits_row + V);
-  penalise(lg, prev, n_prev);
-  const float temp = 0.8;
-  const float kth_raw = kth_largest_50(lg.data());
-  const float kth = kth_raw / temp;  // == s[V - 50] of the divided array (x -> x / temp is monotone)
-  // survivors: !(x / temp < kth).  x >= kth_raw always survives; below it only values whose
-  // quotient rounds up to kth can -- they are within a few ulp of kth_raw.
-  const float slack = std::fabs(kth_raw) * 4e-7f + 1e-37f;
-  const float lo = kth_raw - slack;
-  std::vector<std::pair<float, int>> surv;  // (value / temp, index), in index order
-  surv.reserve(64);
-  auto consider = [&](int i) {
-    const float x = lg[i];
-    if (x >= lo) {
-      const float q = x / temp;
-      if (!(q < kth)) surv.push_back(std::make_pair(q, i));
-    }
-  };
-  for (int i = 0; i < V; ++i) consider(i);
+// Shared tail of the fast paths: top-p, final softmax and the multinomial draw over the top-k
+// survivors `surv` ((value / temp, index) in INDEX order).  Returns -1 when it must defer to the
+// literal path (ties among survivors: the only case where std::sort's unspecified order of equal
+// keys could matter).  Draws from the generator only after it has decided not to defer.
+static int finish_from_survivors(Rng &r, const std::vector<std::pair<float, int>> &surv, float *logprob) {
   std::vector<std::pair<float, int>> asc(surv);
   std::sort(asc.begin(), asc.end());  // by value, then index
   for (size_t i = 1; i < asc.size(); ++i)
     if (asc[i].first == asc[i - 1].first) return -1;
-  if ((int)surv.size() == V) return -1;  // degenerate: nothing was cut
   // top-p over the ascending survivors; the V - |surv| masked entries contribute exact zeros
   // and sort before every survivor, so index i of the full sorted array = i - n_masked here.
   const int ns = int(asc.size());
@@ -184,6 +160,87 @@ static int sample_fast_one(Rng &r, const float *logits_row, const int32_t *prev,
   }
   if (logprob) *logprob = pickp > 0.f ? std::log(pickp) : -std::numeric_limits<float>::infinity();
   return pick;
+}
+
+// returns -1 when it must defer to the literal path
+//
+// Cost matters: the sampler sits between two decode steps (a step is ~0.45 ms on B200, and 16
+// candidates are sampled one after the other).  The 50th-largest value is found with a 50-entry
+// min-heap in ONE pass over the penalised raw logits (division by the temperature is monotone,
+// so it is applied to the handful of candidates around the threshold only; the survivor test
+// itself is done on the divided values exactly as the reference does it).
+static int sample_fast_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev, float *logprob) {
+  thread_local std::vector<float> lg;
+  lg.assign(logits_row, logits_row + V);
+  penalise(lg, prev, n_prev);
+  const float temp = 0.8;
+  const float kth_raw = kth_largest_50(lg.data());
+  const float kth = kth_raw / temp;  // == s[V - 50] of the divided array (x -> x / temp is monotone)
+  // survivors: !(x / temp < kth).  x >= kth_raw always survives; below it only values whose
+  // quotient rounds up to kth can -- they are within a few ulp of kth_raw.
+  const float slack = std::fabs(kth_raw) * 4e-7f + 1e-37f;
+  const float lo = kth_raw - slack;
+  std::vector<std::pair<float, int>> surv;  // (value / temp, index), in index order
+  surv.reserve(64);
+  for (int i = 0; i < V; ++i) {
+    const float x = lg[i];
+    if (x >= lo) {
+      const float q = x / temp;
+      if (!(q < kth)) surv.push_back(std::make_pair(q, i));
+    }
+  }
+  if ((int)surv.size() == V) return -1;  // degenerate: nothing was cut
+  return finish_from_survivors(r, surv, logprob);
+}
+
+// The same sampler fed with the device-side pre-selection (tts_ar_step_topk): `n` (value, index)
+// pairs holding the n largest RAW logits of the row (ties at the cut: lowest indices).  Exactness
+// argument: let m = the smallest raw value among the entries; every entry of the row that is NOT in
+// the set has raw <= m, and the repetition penalty only lowers a value, so after the penalty it is
+// still <= m.  The top-k threshold (50th largest penalised value) computed over the set is >= the
+// (50 + #penalised)-th largest raw value; if m lies strictly below the survivor window
+// [kth_raw - slack, inf) no outside entry can be a survivor, the threshold over the set equals the
+// threshold over the row, and everything downstream only looks at survivors -- the result is the
+// one sample_fast_one produces on the full row.  Returns -2 when that cannot be shown (the caller
+// fetches the full row), -1 on ties among survivors (literal path, also on the full row).
+int sample_sparse_one(Rng &r, const float *vals, const int32_t *idx, int n, const int32_t *prev, int n_prev,
+                      float *logprob) {
+  if (n < 52) return -2;
+  std::vector<std::pair<int, float>> ent(n);  // (index, penalised value), sorted by index below
+  float m = std::numeric_limits<float>::infinity();
+  for (int i = 0; i < n; ++i) {
+    if (idx[i] < 0 || idx[i] >= V) return -2;
+    float x = vals[i];
+    m = std::min(m, x);
+    for (int j = 0; j < n_prev; ++j)
+      if (prev[j] == idx[i]) {  // every scatter derives from the ORIGINAL logit: duplicates are idempotent
+        x = vals[i] < 0 ? vals[i] * 2.0f : vals[i] / 2.0f;
+        break;
+      }
+    ent[i] = std::make_pair(int(idx[i]), x);
+  }
+  std::sort(ent.begin(), ent.end());
+  for (int i = 1; i < n; ++i)
+    if (ent[i].first == ent[i - 1].first) return -2;  // malformed set
+  std::vector<float> pv(n);
+  for (int i = 0; i < n; ++i) pv[i] = ent[i].second;
+  std::nth_element(pv.begin(), pv.begin() + 49, pv.end(), std::greater<float>());
+  const float temp = 0.8;
+  const float kth_raw = pv[49];
+  const float kth = kth_raw / temp;
+  const float slack = std::fabs(kth_raw) * 4e-7f + 1e-37f;
+  const float lo = kth_raw - slack;
+  if (!(m < lo)) return -2;  // an entry outside the set could reach the survivor window
+  std::vector<std::pair<float, int>> surv;
+  surv.reserve(64);
+  for (int i = 0; i < n; ++i) {
+    const float x = ent[i].second;
+    if (x >= lo) {
+      const float q = x / temp;
+      if (!(q < kth)) surv.push_back(std::make_pair(q, ent[i].first));
+    }
+  }
+  return finish_from_survivors(r, surv, logprob);
 }
 
 int sample_one(Rng &r, const float *logits_row, const int32_t *prev, int n_prev, float *logprob) {

@@ -116,9 +116,16 @@ int main(int argc, char **argv) {
   if (bench_json) {
     const double audio_s = audio.size() / 24000.0;
     printf("{\"load_s\": %.3f, \"ar_s\": %.4f, \"diffusion_s\": %.4f, \"vocoder_s\": %.4f, \"audio_s\": %.3f, "
-           "\"rtf\": %.3f, \"ar_steps\": %d, \"candidates\": %d, \"launches\": %lld}\n",
-           t1 - t0, t2 - t1, t3 - t2, t4 - t3, audio_s, audio_s / (t4 - t1), ar_steps, B,
+           "\"rtf\": %.3f, \"ar_steps\": %d, \"candidates\": %d, \"winner\": %d, \"launches\": %lld, \"codes\": [",
+           t1 - t0, t2 - t1, t3 - t2, t4 - t3, audio_s, audio_s / (t4 - t1), ar_steps, B, best,
            (long long)tts_launch_count(ctx));
+    // sampled mel codes of the diffused candidate up to and including the stop token (parity tests)
+    for (int i = 0; i < 500; ++i) {
+      const int code = codes[size_t(best) * 500 + i];
+      printf("%s%d", i ? ", " : "", code);
+      if (code == TTS_MEL_STOP) break;
+    }
+    printf("]}\n");
   }
   tts_free(ctx);
   tts_rng_free(rng);

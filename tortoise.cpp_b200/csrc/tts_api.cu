@@ -114,6 +114,13 @@ int tts_ar_step_dev(tts_ctx *c, const int32_t *tokens, int32_t pos_id, const flo
   TTS_API_BODY(c, if (!tokens) throw tts::ArgError("null argument"); tts::ar_step(c, tokens, pos_id, nullptr, false);
                if (logits_dev) *logits_dev = c->ars.logits)
 }
+int tts_ar_step_topk(tts_ctx *c, const int32_t *tokens, int32_t pos_id, float *vals, int32_t *idx, int32_t *flags) {
+  TTS_API_BODY(c, if (!tokens || !vals || !idx || !flags) throw tts::ArgError("null argument");
+               tts::ar_step_topk(c, tokens, pos_id, vals, idx, flags))
+}
+int tts_ar_logits(tts_ctx *c, float *logits) {
+  TTS_API_BODY(c, if (!logits) throw tts::ArgError("null argument"); tts::ar_logits(c, logits))
+}
 int tts_ar_latents(tts_ctx *c, const int32_t *text, int32_t T, const float *voice, const int32_t *codes, int32_t B,
                    int32_t n_keep, float *out) {
   TTS_API_BODY(c, if (!text || !voice || !codes || !out) throw tts::ArgError("null argument");

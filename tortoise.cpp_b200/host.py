@@ -17,7 +17,7 @@ FULL_LIB_PATH = os.path.join(_HERE, "libtortoise_b200.so")
 
 class AROptions(C.Structure):
     _fields_ = [("max_steps", C.c_int32), ("forced_codes", C.c_int32), ("per_candidate_stop", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("full_logits", C.c_int32)]
 
 
 class HostLib:
@@ -41,6 +41,7 @@ class HostLib:
         lib.tts_host_split_text.argtypes = [C.c_char_p, i32, i32p, i32]
         lib.tts_host_sample.argtypes = [vp, f32p, i32p, i32, i32, i32p, f32p]
         lib.tts_host_sample_reference_order.argtypes = [vp, f32p, i32p, i32, i32, i32p]
+        lib.tts_host_sample_sparse.argtypes = [vp, f32p, i32p, i32, i32p, i32, i32p, f32p]
         lib.tts_host_apply_padding.argtypes = [i32p, i32, i32p]
         lib.tts_host_trim_count.argtypes = [i32p]
         lib.tts_host_write_wav.argtypes = [C.c_char_p, f32p, C.c_int64, i32]
@@ -104,6 +105,19 @@ class HostLib:
             raise RuntimeError(f"sample failed: {rc}")
         return (out, lp) if want_logprob else out
 
+    def sample_sparse(self, rng, vals, idx, prev):
+        """one candidate from (value, index) pairs; returns (sample, logprob) or None when the full row is needed"""
+        vals = np.ascontiguousarray(vals, dtype=np.float32)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        prev = np.ascontiguousarray(prev, dtype=np.int32)
+        out, lp = C.c_int32(), C.c_float()
+        rc = self.lib.tts_host_sample_sparse(rng.h, vals.ctypes.data_as(C.POINTER(C.c_float)),
+                                             idx.ctypes.data_as(C.POINTER(C.c_int32)), len(vals),
+                                             prev.ctypes.data_as(C.POINTER(C.c_int32)), len(prev), C.byref(out), C.byref(lp))
+        if rc < 0:
+            raise ValueError("bad argument")
+        return None if rc == 1 else (out.value, lp.value)
+
     def apply_padding(self, seq):
         seq = np.ascontiguousarray(seq, dtype=np.int32)
         out = np.empty(502, dtype=np.int32)
@@ -145,12 +159,13 @@ class HostLib:
         return out
 
     # ---- stage drivers (full library only)
-    def autoregressive(self, engine, rng, tokens, voice, B, max_steps=0, forced_codes=0, per_candidate_stop=False):
+    def autoregressive(self, engine, rng, tokens, voice, B, max_steps=0, forced_codes=0, per_candidate_stop=False,
+                       full_logits=False):
         assert self.full
         tokens = np.ascontiguousarray(tokens, dtype=np.int32)
         voice = np.ascontiguousarray(voice, dtype=np.float32)
         opt = AROptions(max_steps=max_steps, forced_codes=forced_codes,
-                        per_candidate_stop=1 if per_candidate_stop else 0)
+                        per_candidate_stop=1 if per_candidate_stop else 0, full_logits=1 if full_logits else 0)
         codes = np.empty((B, 500), dtype=np.int32)
         lat = np.empty((B, 500, 1024), dtype=np.float32)
         nlat = np.empty(B, dtype=np.int32)
