@@ -20,6 +20,10 @@
 //   * the K = 4096 phase takes its 8 KB rows two per stage as before, but the 4096-wide f16 hidden
 //     vectors of 16 candidates (128 KB) do not fit beside the ring: candidates are fed to the same
 //     resident weight stages 8 at a time;
+//   * attention keeps ar_mega3's one-CTA-per-(candidate, head) items (two rounds per layer at 16
+//     candidates); a one-WARP-per-item variant (K / V rows straight from L2, no block barrier) measured
+//     SLOWER on B200: 925 -> 1337 us per step at 8 candidates, 1470 -> 1840 at 16
+//     (profiles/r02c_decode_warp_items_ab.txt) -- a single warp's dependent load chain is the longer pole;
 //   * the prompt's K/V rows (identical for every candidate: the reference tiles B identical rows,
 //     main.cpp:2640-2652) are stored ONCE, in candidate slot 0: attention item (b, head) reads rows
 //     [0, n_prefix) from slot 0 and its own rows after that.
@@ -484,18 +488,19 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega4_kernel(M
         const uint32_t tg = tag_of(li, 4);
         if (pass > 0) bar_consumers();  // the previous pass still reads xs / partial
 #pragma unroll 1
-        for (int rnd = 0; rnd < 4; ++rnd) {
-          // round rnd: candidates cb0 + 2 rnd, + 1; thread owns units tid + 256 u (u = 0..3) of each
-          uint4 v[2][4];
+        for (int rnd = 0; rnd < 2; ++rnd) {
+          // round rnd: candidates cb0 + 4 rnd .. + 3; thread owns units tid + 256 u (u = 0..3) of each:
+          // 16 loads in flight per thread (only the first round of a phase really waits)
+          uint4 v[4][4];
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[i][u] = make_uint4(0, ~tg, 0, ~tg);
           for (;;) {
             bool pending = false;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int b = cb0 + 2 * rnd + i;
+            for (int i = 0; i < 4; ++i) {
+              const int b = cb0 + 4 * rnd + i;
               const uint2 *src = a.ll_m + rep * m_rep + size_t(b) * (kFF / 2);
 #pragma unroll
               for (int u = 0; u < 4; ++u)
@@ -507,8 +512,8 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega4_kernel(M
             if (!pending) break;
           }
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int b = cb0 + 2 * rnd + i, bl = 2 * rnd + i;
+          for (int i = 0; i < 4; ++i) {
+            const int b = cb0 + 4 * rnd + i, bl = 4 * rnd + i;
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               *reinterpret_cast<uint2 *>(xs + bl * M4_XP4 + 4 * (tid + u * M2_CONSUMERS)) =

@@ -447,7 +447,7 @@ void diff_step(tts_ctx *c, const float *noise_block) {
        (const float *)m.noise_dev, (const DdpmCoef *)m.coefs, (const int *)m.d_step, S);
     LL(step_inc_kernel, dim3(1), dim3(32), 0, m.d_step);
   };
-  const int launches_per_step = 3 * (8 + 6) + 3 + 10 * (8 + 6) + 3 * 8 + 3 + 2;
+  const int launches_per_step = 125;  // counted on the ncu launch list (profiles/r01d_launches_summary.md)
   if (c->use_graph) {
     if (!m.step_graph || m.graph_S != S) {
       if (m.step_graph) cudaGraphExecDestroy(m.step_graph);

@@ -45,6 +45,15 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// one lane of a CONVERGED warp.  tcgen05.mma / TMA take their operands from uniform registers; issued
+// under `if (lane == 0)` ptxas cannot assume a single active lane and wraps every instruction in an
+// ELECT / R2UR / BRA.U.ANY waterfall loop -- measured ~100-150 cycles of issue time per tcgen05.mma
+// (profiles/r02f_dstep_mma_issue_trace.txt).  With elect.sync the whole warp walks the loop, one lane issues.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 

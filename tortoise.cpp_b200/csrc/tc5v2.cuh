@@ -125,8 +125,8 @@ static __global__ void __launch_bounds__(T6_THREADS, T6_MIN_CTAS)
   if (tid == 0) trace(1);
 
   if (warp == T6_PROD_WARP) {
-    if (lane == 0) {
-      // ================= TMA producer (one thread) =================
+    {
+      // ================= TMA producer (the warp walks the loop, one elected lane issues: see elect_one) =================
       const int a_row0 = seq * (g.T + 2 * g.halo) + t0 + g.halo - g.pad;
       auto load_w = [&](int j) {
         const int it = it0 + j, s = j % stages;
@@ -144,36 +144,46 @@ static __global__ void __launch_bounds__(T6_THREADS, T6_MIN_CTAS)
       };
       const int pre = min(stages, nit);
       for (int j = 0; j < pre; ++j) {  // weights first: they do not depend on the previous kernel
-        mbar_arrive_expect_tx(&full[j], stage_bytes);
-        load_w(j);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[j], stage_bytes);
+          load_w(j);
+        }
+        __syncwarp();
       }
-      trace(2);
+      if (lane == 0) trace(2);
       pdl_wait();
-      trace(3);
-      for (int j = 0; j < pre; ++j) load_a(j);
-      trace(4);
+      if (lane == 0) trace(3);
+      for (int j = 0; j < pre; ++j) {
+        if (elect_one()) load_a(j);
+        __syncwarp();
+      }
+      if (lane == 0) trace(4);
       for (int j = pre; j < nit; ++j) {
         const int s = j % stages;
         mbar_wait(&empty[s], ((j / stages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[s], stage_bytes);
-        load_w(j);
-        load_a(j);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[s], stage_bytes);
+          load_w(j);
+          load_a(j);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == T6_MMA_WARP) {
-    if (lane == 0) {
-      // ================= MMA issuer (one thread) =================
+    {
+      // ================= MMA issuer (the warp walks the loop, one elected lane issues) =================
       const uint32_t idesc = (1u << 4) | (uint32_t(T6_BN >> 3) << 17) | (uint32_t(T6_BM >> 4) << 24);
-      uint32_t acc = 0;
       for (int j = 0; j < nit; ++j) {
         const int s = j % stages;
         mbar_wait(&full[s], (j / stages) & 1);
         tc5_fence_after();
-        if (j == 0) trace(5);
+        if (j == 0 && lane == 0) trace(5);
+        if (elect_one()) {
         const uint32_t sa = smem_u32(base + size_t(s) * stage_bytes);
         const uint32_t sa_lo = sa + T6_PLANE;
         const uint32_t sw = sa + T6_PLANE * a_planes;
         const uint32_t sw_lo = sw + T6_PLANE;
+        uint32_t acc = j > 0 ? 1u : 0u;  // (derived from the iteration, not carried: whichever lane is elected sees it)
 #pragma unroll
         for (int k = 0; k < T6_BK / 16; ++k) {
           const uint32_t koff = k * 32;
@@ -183,9 +193,12 @@ static __global__ void __launch_bounds__(T6_THREADS, T6_MIN_CTAS)
           acc = 1;
         }
         umma_commit(&empty[s]);
+        }
+        __syncwarp();
       }
-      umma_commit(done);
-      trace(6);
+      if (elect_one()) umma_commit(done);
+      __syncwarp();
+      if (lane == 0) trace(6);
     }
   } else {
     // ================= TMEM -> shared partial tile =================
