@@ -130,6 +130,25 @@ int tts_diffusion_end(tts_ctx *ctx, float *mel_out_100xS);
 int tts_vocoder(tts_ctx *ctx, const float *mel_100xS, int32_t S, const float *noise,
                 float *audio_out);
 
+/* ---- multi-GPU: the final candidate gather / selection (the path's only exchange; NCCL) ------------
+ * Candidates are sharded over GPUs (weights replicated, no data-path collective); every rank contributes
+ * (score, n_codes) per candidate to ONE ncclAllGather and the best score wins (first maximum, NaN loses).
+ * The reference has neither a scorer nor a multi-GPU path (main() diffuses candidate 0, main.cpp:6575).
+ * A group is formed either inside one process that owns several contexts (tts_group_init_local,
+ * ncclCommInitAll; what `tortoise --gpus N` does) or with one process per GPU (tts_group_init_rank with a
+ * 128-byte id from tts_nccl_unique_id distributed by the launcher; what bench.py does under torchrun).
+ * libnccl.so.2 is dlopen'ed on first use: TTS_ENODEV when it is absent.  Free the group before its contexts. */
+typedef struct tts_group tts_group;
+int tts_nccl_unique_id(char *out128);
+int tts_group_init_local(tts_ctx **ctxs, int32_t n, tts_group **out);
+int tts_group_init_rank(tts_ctx *ctx, int32_t rank, int32_t world, const char *id128, tts_group **out);
+/* scores / lens: [n_local][per] with n_local = number of LOCAL members (all ranks in local mode, 1 in rank
+ * mode).  *winner = global candidate index rank * per + i; scores_all / lens_all [world][per] (may be NULL). */
+int tts_gather_select(tts_group *g, const float *scores, const int32_t *lens, int32_t per, int32_t *winner,
+                      float *scores_all, int32_t *lens_all);
+const char *tts_group_last_error(const tts_group *g);
+void tts_group_free(tts_group *g);
+
 /* blocks until all work queued by this context has finished (pairs with *_dev calls) */
 int tts_sync(tts_ctx *ctx);
 

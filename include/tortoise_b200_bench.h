@@ -20,6 +20,10 @@ int tts_bench_gemv(tts_ctx *ctx, int32_t op, int32_t B, int32_t iters, float *ms
  * (streamed weights + KV read/append + embeddings + logits). */
 int tts_bench_decode_step(tts_ctx *ctx, int32_t iters, float *ms_per_step, double *bytes_per_step);
 
+/* the denoiser's 3-tap convolution (tcgen05 GEMM, M = 2 S rows, N = K = 1024) on the loaded diffusion
+ * weights: `iters` back-to-back launches between two CUDA events; ms per launch and FLOP per launch */
+int tts_bench_conv3(tts_ctx *ctx, int32_t S, int32_t iters, float *ms_per_launch, double *flop_per_launch);
+
 #ifdef __cplusplus
 }
 #endif

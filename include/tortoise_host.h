@@ -87,6 +87,10 @@ typedef struct tts_ar_options {
   int32_t full_logits;      /* 1 = copy all 8194 logits per candidate to the host every step like the
                                reference (main.cpp:4767); 0 = device-side top-64 pre-selection
                                (tts_ar_step_topk + tts_host_sample_sparse; identical samples)   */
+  int32_t skip_latents;     /* 1 = stop after the codes / scores (latents_out may be NULL): the caller
+                               selects a candidate -- possibly across GPUs, tts_gather_select -- and
+                               runs the latent pass for the winner only (tts_host_latents)       */
+  int32_t reserved[3];
 } tts_ar_options;
 
 /* autoregressive() (main.cpp:5042-5367).  codes_out [B][500] (after apply_padding, without
@@ -96,6 +100,11 @@ typedef struct tts_ar_options {
 int tts_host_autoregressive(struct tts_ctx *ctx, tts_rng *r, const int32_t *tokens, int T, const float *voice_1024,
                             int B, const tts_ar_options *opt, int32_t *codes_out, float *latents_out,
                             int32_t *n_latents, float *score_out, int32_t *steps_out);
+
+/* The latent pass of autoregressive() (main.cpp:5280-5352) + trim_latents (main.cpp:4873-4915) for ONE
+ * candidate's codes500 (as returned in codes_out): latents_out [500][1024], rows >= *n_latents zero. */
+int tts_host_latents(struct tts_ctx *ctx, const int32_t *tokens, int T, const float *voice_1024,
+                     const int32_t *codes500, float *latents_out, int32_t *n_latents);
 
 /* diffusion() (main.cpp:5614-6042): latents [L][1024] -> mel [100][S], S = L*4*24000/22050
  * (integer arithmetic).  mel_out must hold 100*S floats; *S_out receives S. */

@@ -14,8 +14,10 @@ HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 @pytest.mark.skipif(not os.path.exists(HARNESS), reason="oracle/_ref/ref_harness not built (needs /root/reference)")
 def test_reference_arm_prints_one_json_line():
+    # (--ref-sample bounded: the default reference arm runs ONE FULL utterance, ~5 minutes of CPU -- what the
+    # driver measures; the bounded sample exercises the same plumbing in ~40 s)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+                        "--warmup", "0", "--ref-sample", "bounded"], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-500:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -27,6 +29,22 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "configs[1]" in d["config"]["workload"]
+    assert "BOUNDED" in d["cpu_baseline"]["sample"]
+
+
+def test_workload_definitions_match_baseline_configs():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert len(bench.PROMPT_C3) == 50 and len(bench.PROMPT_C4) == 200
+    for name, cand, steps in (("C2", 1, 80), ("C3", 16, 80), ("C4", 8, 200), ("C5", 1, 80)):
+        w = bench.workload(name, 8)
+        assert w["cand"] == cand and w["steps"] == steps and not w["reduced"]
+    assert bench.workload("C4", 8)["codes"] == 300 and bench.workload("C2", 1)["codes"] == 35 and bench.workload("C3", 1)["codes"] == 75
+    ps = bench.c5_prompts()
+    assert len(ps) == 256 and min(map(len, ps)) >= 20 and max(map(len, ps)) <= 300
+    assert all(set(p) <= set("abcdefghijklmnopqrstuvwxyz .,!?'-") for p in ps + [bench.PROMPT_C3, bench.PROMPT_C4])
+    cfg = bench.workload_config(bench.workload("C4", 8), 8)
+    assert "configs[3]" in cfg["workload"] and cfg["global_candidates"] == 64
 
 
 def test_b200_arm_fails_loudly_without_a_gpu():

@@ -139,3 +139,41 @@ def test_forced_length_bench_mode(engine_f32, golden, hostlib_full, voice):
     for b in range(2):
         assert codes[b][12] == 8193 and 8193 not in codes[b][:12]
         assert nlat[b] == 13 + 8
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def test_gather_select_single_rank_group(pkg, engine_f32):
+    """tts_gather_select (NCCL through the C-ABI) on a one-rank group: the winner is the first maximum,
+    NaN scores never win, lengths travel bit-exactly."""
+    g = pkg.Group([engine_f32])
+    try:
+        win, sa, la = g.gather_select(np.array([[0.5, float("nan"), 2.0, 2.0, -1.0]], np.float32), np.array([[7, 8, 9, 10, 11]], np.int32))
+        assert win == 2 and la.tolist() == [[7, 8, 9, 10, 11]] and sa[0, 2] == 2.0 and np.isnan(sa[0, 1])
+    finally:
+        g.close()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_cli_two_gpus_shards_candidates_and_selects_over_nccl(model_dir, tmp_path, pkg):
+    """`tortoise --gpus 2 --candidates 8`: 4 candidates per GPU, one NCCL all-gather for the selection, the
+    winner's owner renders.  GPU 0 keeps the reference's RNG stream, so a winner on GPU 0 reproduces the
+    single-GPU 4-candidate run's codes."""
+    import json
+    exe = os.path.join(os.path.dirname(pkg.LIB_PATH), "tortoise")
+    work = tmp_path / "build"
+    work.mkdir()
+    os.symlink(model_dir, tmp_path / "models")
+    r = subprocess.run([exe, "--seed", "0", "--gpus", "2", "--candidates", "8", "--dtype", "f16", "--bench-json", "x"], cwd=work,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["candidates"] == 8 and 0 <= info["winner"] < 8 and info["codes"][-1] == 8193
+    audio = np.frombuffer((work / "output.wav").read_bytes()[44:], dtype=np.float32)
+    assert np.isfinite(audio).all() and audio.size == ((len(info["codes"]) + 8) * 4 * 24000 // 22050 + 10) * 256 - 6

@@ -83,8 +83,17 @@ def load_library() -> C.CDLL:
     lib.tts_last_stage_ms.restype = C.c_float
     lib.tts_device_ms_total.argtypes = [vp]
     lib.tts_device_ms_total.restype = C.c_double
+    lib.tts_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.tts_group_init_rank.argtypes = [vp, i32, i32, C.c_char_p, P(vp)]
+    lib.tts_group_init_local.argtypes = [P(vp), i32, P(vp)]
+    lib.tts_gather_select.argtypes = [vp, f32p, i32p, i32, i32p, f32p, i32p]
+    lib.tts_group_last_error.argtypes = [vp]
+    lib.tts_group_last_error.restype = C.c_char_p
+    lib.tts_group_free.argtypes = [vp]
+    lib.tts_group_free.restype = None
     lib.tts_bench_decode_step.argtypes = [vp, i32, P(C.c_float), P(C.c_double)]
     lib.tts_bench_gemv.argtypes = [vp, i32, i32, i32, P(C.c_float), P(C.c_double)]
+    lib.tts_bench_conv3.argtypes = [vp, i32, i32, P(C.c_float), P(C.c_double)]
     _lib = lib
     return lib
 
@@ -113,6 +122,7 @@ class Engine:
             raise TTSError(rc, self.lib.tts_last_error(None).decode())
         self.h = h
         self.B = 0
+        self.max_batch = max_batch
 
     def _chk(self, rc):
         if rc != 0:
@@ -236,7 +246,59 @@ class Engine:
         self._chk(self.lib.tts_bench_decode_step(self.h, iters, C.byref(ms), C.byref(by)))
         return ms.value, by.value
 
+    def bench_conv3(self, S, iters):
+        ms, fl = C.c_float(), C.c_double()
+        self._chk(self.lib.tts_bench_conv3(self.h, S, iters, C.byref(ms), C.byref(fl)))
+        return ms.value, fl.value
+
     def bench_gemv(self, op, B, iters):
         ms, by = C.c_float(), C.c_double()
         self._chk(self.lib.tts_bench_gemv(self.h, op, B, iters, C.byref(ms), C.byref(by)))
         return ms.value, by.value
+
+
+def nccl_unique_id() -> bytes:
+    """128 opaque bytes for tts_group_init_rank (rank 0 creates them, the launcher distributes them)"""
+    buf = C.create_string_buffer(128)
+    rc = load_library().tts_nccl_unique_id(buf)
+    if rc != 0:
+        raise TTSError(rc, "tts_nccl_unique_id failed (libnccl.so.2 missing?)")
+    return buf.raw
+
+
+class Group:
+    """Candidate gather / selection over NCCL (include/tortoise_b200.h, csrc/dist.cu)."""
+
+    def __init__(self, engines, rank=None, world=None, unique_id=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if rank is None:  # one process, several GPUs
+            arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+            rc = self.lib.tts_group_init_local(arr, len(engines), C.byref(h))
+            self.n_local, self.world = len(engines), len(engines)
+        else:  # one process per GPU
+            rc = self.lib.tts_group_init_rank(engines[0].h, rank, world, unique_id, C.byref(h))
+            self.n_local, self.world = 1, world
+        if rc != 0:
+            raise TTSError(rc, "NCCL group initialisation failed")
+        self.h = h
+
+    def gather_select(self, scores, lens):
+        """scores / lens: [n_local][per] -> (winner global index, scores_all [world][per], lens_all)"""
+        scores = np.ascontiguousarray(scores, dtype=np.float32).reshape(self.n_local, -1)
+        lens = np.ascontiguousarray(lens, dtype=np.int32).reshape(self.n_local, -1)
+        per = scores.shape[1]
+        win = C.c_int32()
+        sa = np.empty((self.world, per), dtype=np.float32)
+        la = np.empty((self.world, per), dtype=np.int32)
+        rc = self.lib.tts_gather_select(self.h, scores.ctypes.data_as(C.POINTER(C.c_float)),
+                                        lens.ctypes.data_as(C.POINTER(C.c_int32)), per, C.byref(win),
+                                        sa.ctypes.data_as(C.POINTER(C.c_float)), la.ctypes.data_as(C.POINTER(C.c_int32)))
+        if rc != 0:
+            raise TTSError(rc, self.lib.tts_group_last_error(self.h).decode())
+        return win.value, sa, la
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tts_group_free(self.h)
+            self.h = None

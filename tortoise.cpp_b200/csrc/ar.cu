@@ -471,6 +471,18 @@ static void build_step_graph(tts_ctx *c, int B) {
     throw;
   }
   TTS_CUDA_TRY(cudaStreamEndCapture(c->stream, &graph));
+  {  // kernel nodes of the captured step: what one replay launches (the launch counter is a count)
+    size_t n = 0;
+    TTS_CUDA_TRY(cudaGraphGetNodes(graph, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (n) TTS_CUDA_TRY(cudaGraphGetNodes(graph, nodes.data(), &n));
+    s.step_graph_kernels = 0;
+    for (size_t i = 0; i < n; ++i) {
+      cudaGraphNodeType t;
+      TTS_CUDA_TRY(cudaGraphNodeGetType(nodes[i], &t));
+      if (t == cudaGraphNodeTypeKernel) ++s.step_graph_kernels;
+    }
+  }
   TTS_CUDA_TRY(cudaGraphInstantiate(&s.step_graph, graph, 0));
   cudaGraphDestroy(graph);
   s.step_graph_B = B;
@@ -492,7 +504,6 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
   for (int b = 0; b < B; ++b) s.h_tokens[b] = tokens[b];
   s.h_state[0] = s.n_past;
   s.h_state[1] = pos_id;
-  const int launches_per_step = 2 + kLayers * 5;
   TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
   if (mega) {
     {  // tokens travel as kernel parameters (no pinned staging to race with an asynchronous caller)
@@ -510,7 +521,7 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
   } else if (c->use_graph) {
     if (!s.step_graph || s.step_graph_B != B) build_step_graph(c, B);
     TTS_CUDA_TRY(cudaGraphLaunch(s.step_graph, c->stream));
-    c->launches += launches_per_step;
+    c->launches += s.step_graph_kernels;
   } else {
     Launcher L{c->stream, c->use_pdl, &c->launches};
     TTS_CUDA_TRY(cudaMemcpyAsync(s.d_tokens, s.h_tokens, B * 4, cudaMemcpyHostToDevice, c->stream));

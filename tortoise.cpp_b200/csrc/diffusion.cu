@@ -48,6 +48,7 @@ struct DiffModel {
   int *d_step = nullptr;           // device-side sampling-step counter (graph replay)
   cudaGraphExec_t step_graph = nullptr;
   int graph_S = -1;
+  int graph_kernels = 0;           // kernel nodes of step_graph (what one replay launches)
   size_t noise_cap = 0;
   int run_S = 0, run_steps = 0, run_i = -1;  // streaming sampler state
   double *gn_partial = nullptr;    // fused GroupNorm statistics written by the last GEMM epilogue
@@ -388,6 +389,46 @@ void diff_eps(tts_ctx *c, const float *latents, int Lf, const float *x, int S, i
 // Streaming form of the sampling loop: begin (conditioning, schedule, x0) / step (upload the
 // step's noise block, enqueue the captured step graph -- asynchronous) / end (read the mel).
 // The host draws noise block i+1 from the reference's RNG stream while the GPU runs step i.
+// kernel nodes of a captured graph: what one replay launches (the launch counter is a count, not an estimate)
+static int count_kernel_nodes(cudaGraph_t graph) {
+  size_t n = 0;
+  TTS_CUDA_TRY(cudaGraphGetNodes(graph, nullptr, &n));
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (n) TTS_CUDA_TRY(cudaGraphGetNodes(graph, nodes.data(), &n));
+  int k = 0;
+  for (size_t i = 0; i < n; ++i) {
+    cudaGraphNodeType t;
+    TTS_CUDA_TRY(cudaGraphNodeGetType(nodes[i], &t));
+    if (t == cudaGraphNodeTypeKernel) ++k;
+  }
+  return k;
+}
+
+// Measurement only (tortoise_b200_bench.h): the denoiser's 3-tap convolution -- the GEMM shape the diffusion
+// stage spends most of its time in -- `iters` back-to-back launches on the model's own weights between two
+// CUDA events.  M = 2 S rows (cond + uncond), N = K = 1024.
+void diff_bench_conv3(tts_ctx *c, int S, int iters, float *ms, double *flop) {
+  if (!c->diff || !c->diff->loaded) throw ArgError("diffusion model not loaded");
+  if (S < 8 || S > 4096 || iters < 1) throw ArgError("bad argument");
+  DiffModel &m = *c->diff;
+  ensure_buffers(c, S, 1);
+  int64_t dummy = 0;
+  Launcher L{c->stream, c->use_pdl, &dummy};
+  TTS_CUDA_TRY(cudaMemsetAsync(m.A16, 0, size_t(2) * (S + 2) * kDim * 2, c->stream));
+  m.partial_src = nullptr;
+  for (int i = 0; i < 3; ++i) conv(c, L, m.A16, m.res[3 + i].w_out3, m.res[3 + i].b_out3, m.H1, 2, S, kDim, kDim, 3, kDim, E_BIAS);
+  TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  for (int i = 0; i < iters; ++i) conv(c, L, m.A16, m.res[3 + i % 13].w_out3, m.res[3 + i % 13].b_out3, m.H1, 2, S, kDim, kDim, 3, kDim, E_BIAS);
+  TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  float t = 0;
+  TTS_CUDA_TRY(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+  m.partial_src = nullptr;
+  *ms = t / iters;
+  *flop = 2.0 * (2.0 * S) * kDim * kDim * 3;
+  c->launches += iters + 3;
+}
+
 void diff_begin(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, const float *x0) {
   check_sizes(c, Lf, S);
   if (n_steps < 1 || n_steps > 4000) throw ArgError("bad n_steps");
@@ -447,7 +488,6 @@ void diff_step(tts_ctx *c, const float *noise_block) {
        (const float *)m.noise_dev, (const DdpmCoef *)m.coefs, (const int *)m.d_step, S);
     LL(step_inc_kernel, dim3(1), dim3(32), 0, m.d_step);
   };
-  const int launches_per_step = 125;  // counted on the ncu launch list (profiles/r01d_launches_summary.md)
   if (c->use_graph) {
     if (!m.step_graph || m.graph_S != S) {
       if (m.step_graph) cudaGraphExecDestroy(m.step_graph);
@@ -466,12 +506,13 @@ void diff_step(tts_ctx *c, const float *noise_block) {
         throw;
       }
       TTS_CUDA_TRY(cudaStreamEndCapture(c->stream, &graph));
+      m.graph_kernels = count_kernel_nodes(graph);
       TTS_CUDA_TRY(cudaGraphInstantiate(&m.step_graph, graph, 0));
       cudaGraphDestroy(graph);
       m.graph_S = S;
     }
     TTS_CUDA_TRY(cudaGraphLaunch(m.step_graph, c->stream));
-    c->launches += launches_per_step;
+    c->launches += m.graph_kernels;
   } else {
     enqueue_step(L);
   }

@@ -79,6 +79,7 @@ struct ArState {
   // CUDA graph of one decode step, keyed by B
   cudaGraphExec_t step_graph = nullptr;
   int step_graph_B = 0;
+  int step_graph_kernels = 0;
 };
 
 struct DiffModel;
@@ -166,6 +167,7 @@ void diff_begin(tts_ctx *c, const float *latents, int L, int S, int n_steps, con
 void diff_step(tts_ctx *c, const float *noise_block);
 void diff_end(tts_ctx *c, float *mel);
 void diff_free(tts_ctx *c);
+void diff_bench_conv3(tts_ctx *c, int S, int iters, float *ms, double *flop);
 void voc_load(tts_ctx *c, const char *path);
 void voc_run(tts_ctx *c, const float *mel, int S, const float *noise, float *audio);
 void voc_free(tts_ctx *c);

@@ -22,9 +22,10 @@ extern "C" {
 int tts_host_autoregressive(struct tts_ctx *ctx, tts_rng *rng, const int32_t *tokens, int T, const float *voice,
                             int B, const tts_ar_options *opt_in, int32_t *codes_out, float *latents_out,
                             int32_t *n_latents, float *score_out, int32_t *steps_out) {
-  if (!ctx || !rng || !tokens || !voice || !codes_out || !latents_out || !n_latents || B < 1) return TTS_EINVAL;
+  if (!ctx || !rng || !tokens || !voice || !codes_out || !n_latents || B < 1) return TTS_EINVAL;
   tts_ar_options opt{};
   if (opt_in) opt = *opt_in;
+  if (!latents_out && !opt.skip_latents) return TTS_EINVAL;
   const int V = TTS_MEL_VOCAB, STOP = TTS_MEL_STOP;
   std::vector<float> logits(size_t(B) * V);
   int rc = tts_ar_prefill(ctx, tokens, T, voice, B, logits.data());
@@ -120,10 +121,27 @@ int tts_host_autoregressive(struct tts_ctx *ctx, tts_rng *rng, const int32_t *to
     if (n_latents[b] > n_keep) n_keep = n_latents[b];
     if (score_out) score_out[b] = lp_n[b] ? float(lp_sum[b] / lp_n[b]) : 0.f;
   }
+  // candidate selection first, latent pass for the winner only (tts_host_latents): multi-candidate / multi-GPU drivers
+  if (opt.skip_latents) return TTS_OK;
   rc = tts_ar_latents(ctx, tokens, T, voice, codes502.data(), B, n_keep, latents_out);
   if (rc != TTS_OK) return rc;
   for (int b = 0; b < B; ++b)  // zero the rows trim_latents would not return
     memset(latents_out + (size_t(b) * 500 + n_latents[b]) * 1024, 0, size_t(500 - n_latents[b]) * 1024 * 4);
+  return TTS_OK;
+}
+
+int tts_host_latents(struct tts_ctx *ctx, const int32_t *tokens, int T, const float *voice, const int32_t *codes500,
+                     float *latents_out, int32_t *n_latents) {
+  if (!ctx || !tokens || !voice || !codes500 || !latents_out || !n_latents) return TTS_EINVAL;
+  std::vector<int32_t> codes502(502);
+  codes502[0] = TTS_MEL_START;
+  memcpy(codes502.data() + 1, codes500, 500 * 4);
+  codes502[501] = TTS_MEL_STOP;
+  const int n = tts_host::trim_count(codes500);
+  *n_latents = n;
+  const int rc = tts_ar_latents(ctx, tokens, T, voice, codes502.data(), 1, n, latents_out);
+  if (rc != TTS_OK) return rc;
+  memset(latents_out + size_t(n) * 1024, 0, size_t(500 - n) * 1024 * 4);
   return TTS_OK;
 }
 

@@ -157,6 +157,10 @@ int tts_bench_gemv(tts_ctx *c, int32_t op, int32_t B, int32_t iters, float *ms, 
   TTS_API_BODY(c, if (!ms || !bytes || iters < 1) throw tts::ArgError("bad argument"); tts::ar_bench_gemv(c, op, B, iters, ms, bytes))
 }
 
+int tts_bench_conv3(tts_ctx *c, int32_t S, int32_t iters, float *ms, double *flop) {
+  TTS_API_BODY(c, if (!ms || !flop) throw tts::ArgError("bad argument"); tts::diff_bench_conv3(c, S, iters, ms, flop))
+}
+
 int tts_bench_decode_step(tts_ctx *c, int32_t iters, float *ms, double *bytes) {
   TTS_API_BODY(c, if (!ms || !bytes) throw tts::ArgError("bad argument"); tts::ar_bench_step(c, iters, ms, bytes))
 }

@@ -17,7 +17,7 @@ FULL_LIB_PATH = os.path.join(_HERE, "libtortoise_b200.so")
 
 class AROptions(C.Structure):
     _fields_ = [("max_steps", C.c_int32), ("forced_codes", C.c_int32), ("per_candidate_stop", C.c_int32),
-                ("full_logits", C.c_int32)]
+                ("full_logits", C.c_int32), ("skip_latents", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class HostLib:
@@ -53,6 +53,7 @@ class HostLib:
             lib.tts_host_autoregressive.argtypes = [vp, vp, i32p, i32, f32p, i32, P(AROptions), i32p, f32p, i32p,
                                                     f32p, i32p]
             lib.tts_host_diffusion.argtypes = [vp, vp, f32p, i32, i32, f32p, i32p]
+            lib.tts_host_latents.argtypes = [vp, i32p, i32, f32p, i32p, f32p, i32p]
             lib.tts_host_vocoder.argtypes = [vp, vp, f32p, i32, f32p]
         self.lib = lib
         self.full = full
@@ -160,14 +161,15 @@ class HostLib:
 
     # ---- stage drivers (full library only)
     def autoregressive(self, engine, rng, tokens, voice, B, max_steps=0, forced_codes=0, per_candidate_stop=False,
-                       full_logits=False):
+                       full_logits=False, skip_latents=False):
         assert self.full
         tokens = np.ascontiguousarray(tokens, dtype=np.int32)
         voice = np.ascontiguousarray(voice, dtype=np.float32)
         opt = AROptions(max_steps=max_steps, forced_codes=forced_codes,
-                        per_candidate_stop=1 if per_candidate_stop else 0, full_logits=1 if full_logits else 0)
+                        per_candidate_stop=1 if per_candidate_stop else 0, full_logits=1 if full_logits else 0,
+                        skip_latents=1 if skip_latents else 0)
         codes = np.empty((B, 500), dtype=np.int32)
-        lat = np.empty((B, 500, 1024), dtype=np.float32)
+        lat = np.empty((1 if skip_latents else B, 500, 1024), dtype=np.float32)
         nlat = np.empty(B, dtype=np.int32)
         score = np.empty(B, dtype=np.float32)
         steps = C.c_int32()
@@ -179,6 +181,21 @@ class HostLib:
         if rc != 0:
             raise RuntimeError(f"tts_host_autoregressive failed ({rc}): {engine.lib.tts_last_error(engine.h).decode()}")
         return codes, lat, nlat, score, steps.value
+
+    def latents(self, engine, tokens, voice, codes500):
+        """latent pass + trim for one candidate: returns [n][1024]"""
+        assert self.full
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        voice = np.ascontiguousarray(voice, dtype=np.float32)
+        codes500 = np.ascontiguousarray(codes500, dtype=np.int32)
+        lat = np.empty((500, 1024), dtype=np.float32)
+        n = C.c_int32()
+        f32p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        rc = self.lib.tts_host_latents(engine.h, tokens.ctypes.data_as(i32p), len(tokens), voice.ctypes.data_as(f32p),
+                                       codes500.ctypes.data_as(i32p), lat.ctypes.data_as(f32p), C.byref(n))
+        if rc != 0:
+            raise RuntimeError(f"tts_host_latents failed ({rc}): {engine.lib.tts_last_error(engine.h).decode()}")
+        return lat[:n.value]
 
     def diffusion(self, engine, rng, latents, n_steps=80):
         assert self.full
