@@ -144,15 +144,15 @@ def test_c_abi_exports_every_declared_symbol():
     import _pkg
     pkg = _pkg.import_pkg()
     decl = {}
-    for hdr in ("tortoise_b200.h", "tortoise_host.h"):
+    for hdr in ("tortoise_b200.h", "tortoise_host.h", "tortoise_b200_bench.h"):
         src = open(os.path.join(ROOT, "include", hdr)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         decl[hdr] = set(re.findall(r"\b(tts_[a-z0-9_]+)\s*\(", src))
     full = ctypes.CDLL(pkg.LIB_PATH)
-    for name in sorted(decl["tortoise_b200.h"] | decl["tortoise_host.h"]):
+    for name in sorted(decl["tortoise_b200.h"] | decl["tortoise_host.h"] | decl["tortoise_b200_bench.h"]):
         assert hasattr(full, name), f"libtortoise_b200.so lacks {name}"
     host = ctypes.CDLL(os.path.join(os.path.dirname(pkg.LIB_PATH), "libtortoise_host.so"))
-    drivers = {"tts_host_autoregressive", "tts_host_diffusion", "tts_host_vocoder"}
+    drivers = {"tts_host_autoregressive", "tts_host_diffusion", "tts_host_vocoder", "tts_host_latents"}
     for name in sorted(decl["tortoise_host.h"] - drivers):
         assert hasattr(host, name), f"libtortoise_host.so lacks {name}"
 

@@ -10,14 +10,14 @@ namespace tts {
 // GroupNorm statistics, 32 groups x 32 channels over all T frames (ggml_group_norm,
 // ggml.c:12229-12304: eps 1e-6, double sums, mean subtracted in float before squaring).
 // X [nseq][T][1024]; stats[(seq*32+g)*2] = {mean, 1/sqrt(var+eps)}.  grid (32, nseq) x 256.
-static __global__ void __launch_bounds__(256) gn_stats_kernel(const float *X, float *stats, int T) {
+static __global__ void __launch_bounds__(256) gn_stats_kernel(const float *X, float *stats, int T, const int *Tseq) {
   __shared__ double red[8];
   __shared__ float s_mean;
   pdl_launch_dependents();
   pdl_wait();
   const int g = blockIdx.x, seq = blockIdx.y, tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const float *base = X + size_t(seq) * T * kDim + g * 32;
-  const int n = T * 32;
+  const int n = (Tseq ? Tseq[seq] : T) * 32;  // rows past the sequence's own length are padding
   double s = 0;
   for (int i = tid; i < n; i += 256) s += double(base[size_t(i >> 5) * kDim + (i & 31)]);
   s = warp_sum_d(s);
@@ -61,7 +61,7 @@ static __global__ void __launch_bounds__(256) gn_apply_kernel(const float *X, co
                                                        const float *b, const float *ss, __half *out16,
                                                        float *out32, int T, int halo, int ldo, int silu,
                                                        const int *step_ptr, int ss_step_stride,
-                                                       const double *partial, int mtiles) {
+                                                       const double *partial, int mtiles, const int *Tseq) {
   pdl_launch_dependents();
   pdl_wait();
   // the per-timestep scale|shift table advances with a device-side step counter so that one
@@ -70,8 +70,9 @@ static __global__ void __launch_bounds__(256) gn_apply_kernel(const float *X, co
   const int row = blockIdx.x, seq = blockIdx.y, tid = threadIdx.x;
   const int t = row - halo;
   const int c = tid * 4;
+  const int Ts = Tseq ? Tseq[seq] : T;  // valid frames of this sequence (T is the common row stride)
   float v[4] = {0.f, 0.f, 0.f, 0.f};
-  if (t >= 0 && t < T) {
+  if (t >= 0 && t < Ts) {
     const float4 x = *reinterpret_cast<const float4 *>(X + (size_t(seq) * T + t) * kDim + c);
     const int g = c >> 5;
     float mean, rstd;
@@ -82,7 +83,7 @@ static __global__ void __launch_bounds__(256) gn_apply_kernel(const float *X, co
         s1 += partial[((size_t(seq) * 32 + g) * mtiles + i) * 2];
         s2 += partial[((size_t(seq) * 32 + g) * mtiles + i) * 2 + 1];
       }
-      const double n = double(T) * 32.0, md = s1 / n;
+      const double n = double(Ts) * 32.0, md = s1 / n;
       mean = float(md);
       double var = s2 / n - 2.0 * md * double(mean) + double(mean) * double(mean);  // E[(x - mean_f)^2]
       if (var < 0.0) var = 0.0;
@@ -117,7 +118,7 @@ static __global__ void __launch_bounds__(256) gn_apply_kernel(const float *X, co
     *reinterpret_cast<uint2 *>(out16 + (size_t(seq) * (T + 2 * halo) + row) * ldo + c) =
         *reinterpret_cast<uint2 *>(h);
   }
-  if (out32 && t >= 0 && t < T)
+  if (out32 && t >= 0 && t < Ts)
     *reinterpret_cast<float4 *>(out32 + (size_t(seq) * T + t) * kDim + c) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
@@ -136,25 +137,31 @@ static __global__ void __launch_bounds__(256) to_f16_halo_kernel(const float *X,
 }
 
 // x [100][S] (channel-major, the reference's noise_tensor layout) -> f16 [S + 2][128]
-static __global__ void __launch_bounds__(128) xin_kernel(const float *x, __half *out, int S) {
+// Utterance batching: grid.y = utterance u; x of utterance u starts at x + xoff[u] with ITS OWN S_u (the
+// noise blocks keep the reference's [100][S_u] layout), out rows use the common stride S.
+static __global__ void __launch_bounds__(128) xin_kernel(const float *x, __half *out, int S, const int *Sutt, const long long *xoff) {
   pdl_launch_dependents();
   pdl_wait();
-  const int row = blockIdx.x, t = row - 1, c = threadIdx.x;
+  const int row = blockIdx.x, u = blockIdx.y, t = row - 1, c = threadIdx.x;
+  const int Su = Sutt ? Sutt[u] : S;
+  const float *xu = x + (xoff ? xoff[u] : 0);
   float v = 0.f;
-  if (t >= 0 && t < S && c < 100) v = x[size_t(c) * S + t];
-  out[size_t(row) * 128 + c] = __float2half_rn(v);
+  if (t >= 0 && t < Su && c < 100) v = xu[size_t(c) * Su + t];
+  out[(size_t(u) * (S + 2) + row) * 128 + c] = __float2half_rn(v);
 }
 
 // CAT16[seq][t+1][0:1024] = f16(INP[t]), [1024:2048] = f16(CW[seq][t])  (channel concat,
 // main.cpp:3635-3637), halo rows zero.  grid (S + 2, nseq) x 256
-static __global__ void __launch_bounds__(256) concat_kernel(const float *INP, const float *CW, __half *out, int S) {
+// (sequence seq = 2 u + {0 cond, 1 uncond}: both read the input-block output of utterance u = seq / 2)
+static __global__ void __launch_bounds__(256) concat_kernel(const float *INP, const float *CW, __half *out, int S, const int *Tseq) {
   pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x, seq = blockIdx.y, t = row - 1, tid = threadIdx.x;
+  const int Ts = Tseq ? Tseq[seq] : S;
   __half *o = out + (size_t(seq) * (S + 2) + row) * 2048;
   for (int c = tid; c < 2048; c += 256) {
     float v = 0.f;
-    if (t >= 0 && t < S) v = c < 1024 ? INP[size_t(t) * kDim + c] : CW[(size_t(seq) * S + t) * kDim + c - 1024];
+    if (t >= 0 && t < Ts) v = c < 1024 ? INP[(size_t(seq >> 1) * S + t) * kDim + c] : CW[(size_t(seq) * S + t) * kDim + c - 1024];
     o[c] = __float2half_rn(v);
   }
 }
@@ -162,14 +169,17 @@ static __global__ void __launch_bounds__(256) concat_kernel(const float *INP, co
 // nearest-neighbour stretch L -> S (ggml_upscale_ext, ggml.c:15527-15568; index table built
 // on the host with the reference's float arithmetic) and the unconditioned broadcast
 // (main.cpp:3321-3328).  CE [2][S][1024].  grid (S, 2) x 256
+// (CE points at the two sequences of ONE utterance; S is the common row stride, St its own length)
 static __global__ void __launch_bounds__(256) code_emb_kernel(const float *CL, const int *src_idx, const float *uncond,
-                                                       float *CE, int S) {
+                                                       float *CE, int S, int St) {
   pdl_launch_dependents();
   pdl_wait();
   const int t = blockIdx.x, seq = blockIdx.y, c = threadIdx.x * 4;
-  float4 v;
-  if (seq == 0) v = *reinterpret_cast<const float4 *>(CL + size_t(src_idx[t]) * kDim + c);
-  else v = *reinterpret_cast<const float4 *>(uncond + c);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < St) {
+    if (seq == 0) v = *reinterpret_cast<const float4 *>(CL + size_t(src_idx[t]) * kDim + c);
+    else v = *reinterpret_cast<const float4 *>(uncond + c);
+  }
   *reinterpret_cast<float4 *>(CE + (size_t(seq) * S + t) * kDim + c) = v;
 }
 
@@ -197,7 +207,7 @@ static __global__ void silu_split_kernel(const float *in, __half *hi, __half *lo
 constexpr int DA_WARPS = 8, DA_THREADS = DA_WARPS * 32, DA_Q = DA_WARPS * 4, DA_TK = 64, DA_LDK = kHeadDim + 4;
 constexpr size_t DA_SMEM = (size_t(2) * DA_TK * DA_LDK + size_t(DA_Q) * kHeadDim + size_t(DA_WARPS) * 4 * DA_TK + 32) * sizeof(float);
 static __global__ void __launch_bounds__(DA_THREADS) diff_attn_kernel(const float *QKV, const float *relbias, const int *rpb,
-                                                               __half *out_hi, __half *out_lo, int T) {
+                                                               __half *out_hi, __half *out_lo, int Tstride, const int *Tseq) {
   constexpr int TK = DA_TK, LDK = DA_LDK;
   extern __shared__ __align__(16) float da_smem[];
   float (*Ks)[LDK] = reinterpret_cast<float (*)[LDK]>(da_smem);
@@ -210,7 +220,9 @@ static __global__ void __launch_bounds__(DA_THREADS) diff_attn_kernel(const floa
   const int t = threadIdx.x, warp = t / 32, lane = t % 32;
   const int head = blockIdx.y, seq = blockIdx.z;
   const int q0 = blockIdx.x * DA_Q;
-  const float *base = QKV + size_t(seq) * T * 3072 + head * 192;
+  const int T = Tseq ? Tseq[seq] : Tstride;  // this sequence's own length (keys / queries past it are padding)
+  if (q0 >= T) return;
+  const float *base = QKV + size_t(seq) * Tstride * 3072 + head * 192;
   if (t < 32) bias_s[t] = 8.0f * relbias[t * 16 + head];
   for (int i = t; i < DA_Q * kHeadDim; i += DA_THREADS) {
     const int r = i / kHeadDim, d = i % kHeadDim;
@@ -312,16 +324,22 @@ struct DdpmCoef {
   float cfk, sqrt_recip, sqrt_recipm1, coef1, coef2, min_log, max_log;
   int last;
 };
+// Utterance batching (grid.y = utterance u): x of utterance u at x + xoff[u] in ITS OWN [100][S_u] layout, its
+// noise at noise_base + noff[u] + (step + 1) * 100 * S_u, its model outputs in sequences 2u / 2u + 1 (row stride S).
 static __global__ void __launch_bounds__(256) ddpm_step_kernel(float *x, const float *OUT, const float *noise_base,
-                                                        const DdpmCoef *coefs, const int *step_ptr, int S) {
+                                                        const DdpmCoef *coefs, const int *step_ptr, int S, const int *Sutt,
+                                                        const long long *xoff, const long long *noff) {
   pdl_launch_dependents();
   pdl_wait();
-  const int step = *step_ptr;
+  const int step = *step_ptr, u = blockIdx.y;
   const DdpmCoef k = coefs[step];
-  const int n = 100 * S;
-  const float *noise = noise_base + size_t(step + 1) * n;  // block 0 was the initial x
+  const int Su = Sutt ? Sutt[u] : S;
+  const int n = 100 * Su;
+  x += xoff ? xoff[u] : 0;
+  OUT += size_t(2 * u) * S * 200;
+  const float *noise = noise_base + (noff ? noff[u] : 0) + size_t(step + 1) * n;  // block 0 was the initial x
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int ch = i / S, t = i % S;
+    const int ch = i / Su, t = i % Su;
     const float eps_c = OUT[size_t(t) * 200 + ch];
     const float vraw = OUT[size_t(t) * 200 + 100 + ch];
     const float eps_u = OUT[(size_t(S) + t) * 200 + ch];

@@ -177,6 +177,10 @@ struct TGemmArgs {
   double *gn_partial;
   int gn_mtiles;
   long long *dbg;  // optional per-launch clock trace (TTS_TC5_TRACE=1), else null
+  // optional per-sequence valid lengths (utterance batching: sequences of different lengths share the row
+  // stride T; rows >= Tseq[seq] are padding -- neither stored nor counted in the GroupNorm statistics).
+  // tcgen05 path (tc5v2.cuh) only.
+  const int *Tseq;
 };
 
 constexpr int TG_BM = 64, TG_BN = 64, TG_BK = 32, TG_LD = TG_BK + 8, TG_STAGES = 3;

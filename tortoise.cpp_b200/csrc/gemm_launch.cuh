@@ -31,6 +31,7 @@ static inline bool tc5_v1_forced() {
 static inline int launch_gemm(const Launcher &L, const TGemmArgs &g_in) {
   TGemmArgs g = g_in;
   if (tc5_enabled() && !tc5_v1_forced() && tc5v2_supported(g)) return launch_tc5v2(L, g);
+  if (g.Tseq) throw ArgError("internal: per-sequence lengths need the tcgen05 GEMM path");
   if (tc5_enabled() && g.K % T5_BK == 0) {
     const bool alo = g.Alo != nullptr, wlo = g.Wlo != nullptr;
     const int nseq = g.M / g.T;                      // M = nseq * T always

@@ -87,7 +87,7 @@ static __global__ void __launch_bounds__(T6_THREADS, T6_MIN_CTAS)
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int rank = blockIdx.z % csz, seq = blockIdx.z / csz;
   const int t0 = blockIdx.y * T6_BM;
-  const int rows_valid = min(T6_BM, g.T - t0);
+  const int rows_valid = max(0, min(T6_BM, (g.Tseq ? g.Tseq[seq] : g.T) - t0));
   const int m0 = seq * g.T + t0, n0 = blockIdx.x * T6_BN;
   const int kchunks = g.K / T6_BK;
   const int iters = g.taps * kchunks;
