@@ -123,6 +123,16 @@ int tts_diffusion_begin(tts_ctx *ctx, const float *latents, int32_t L, int32_t S
 int tts_diffusion_step(tts_ctx *ctx, const float *noise_block_100xS);
 int tts_diffusion_end(tts_ctx *ctx, float *mel_out_100xS);
 
+/* The same loop for a BATCH of U utterances of different lengths (BASELINE configs[4], utterance batching;
+ * the reference renders one utterance per process): utterance u has latents[u] [L[u]][1024], S[u] mel frames
+ * and its own noise stream (x0[u] / noise_blocks[u] = 100 * S[u] normals each, drawn by the host in the
+ * reference's order from that utterance's generator).  One launch set serves all of them: the GEMMs see
+ * 2 * sum(S[u]) rows.  Results equal the one-at-a-time calls up to f32 summation order. */
+int tts_diffusion_begin_batch(tts_ctx *ctx, int32_t U, const float *const *latents, const int32_t *L, const int32_t *S,
+                              int32_t n_steps, const float *const *x0);
+int tts_diffusion_step_batch(tts_ctx *ctx, const float *const *noise_blocks);
+int tts_diffusion_end_batch(tts_ctx *ctx, float *const *mel_out);
+
 /* ---- vocoder stage ----------------------------------------------------------------- */
 /* Replaces vocoder_graph + compute (main.cpp:6078-6122): mel [100][S] NORMALISED
  * (denormalisation main.cpp:5575 is done on the device), noise [(S+10)][64] as drawn by

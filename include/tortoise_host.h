@@ -111,6 +111,11 @@ int tts_host_latents(struct tts_ctx *ctx, const int32_t *tokens, int T, const fl
 int tts_host_diffusion(struct tts_ctx *ctx, tts_rng *r, const float *latents, int L, int n_steps, float *mel_out,
                        int32_t *S_out);
 
+/* diffusion() for U utterances at once (utterance batching): rngs[u] is utterance u's own generator (each is
+ * consumed exactly as tts_host_diffusion would), mel_out[u] holds 100 * S_out[u] floats. */
+int tts_host_diffusion_batch(struct tts_ctx *ctx, tts_rng *const *rngs, int U, const float *const *latents, const int32_t *L,
+                             int n_steps, float *const *mel_out, int32_t *S_out);
+
 /* vocoder() (main.cpp:6044-6127): mel [100][S] -> audio [(S+10)*256-6] */
 int tts_host_vocoder(struct tts_ctx *ctx, tts_rng *r, const float *mel, int S, float *audio_out);
 

@@ -57,3 +57,28 @@ def test_stage_driver_reproduces_reference_mel(engine_f32, golden, hostlib_full)
 def test_bad_sizes_are_errors(engine_f32, pkg):
     with pytest.raises(pkg.TTSError):
         engine_f32.diffusion_eps(np.zeros((10, 1024), np.float32), np.zeros((100, 5), np.float32), 10, False)
+
+
+def test_utterance_batch_matches_reference_and_one_at_a_time(engine_f32, golden, hostlib_full):
+    """Utterance batching (BASELINE configs[4]): three utterances of different lengths on ONE launch set
+    (sequences share a row stride and carry their own lengths).  Utterance 0 is the reference run itself
+    (seed 0, golden latents): its mel must meet the reference bar; every utterance must equal its own
+    one-at-a-time run up to f32 summation order."""
+    g = golden("diffusion.npz")
+    lat0 = g["latents"].reshape(-1, 1024)
+    rs = np.random.RandomState(7)
+    lats = [lat0, (0.8 * lat0[:17]).astype(np.float32), (0.5 * rs.randn(41, 1024)).astype(np.float32)]
+    seeds = [0, 11, 12]
+    singles = [hostlib_full.diffusion(engine_f32, hostlib_full.rng(s), l, 80) for s, l in zip(seeds, lats)]
+    batch = hostlib_full.diffusion_batch(engine_f32, [hostlib_full.rng(s) for s in seeds], lats, 80)
+    assert [b.shape for b in batch] == [s.shape for s in singles]
+    err0 = np.abs(batch[0] - g["mel"]).max()
+    print(f"batched utterance 0 vs reference mel: max-abs {err0:.3e} nmse {nmse(batch[0], g['mel']):.3e}")
+    assert err0 < TOL or nmse(batch[0], g["mel"]) < 1e-4
+    for u in range(3):
+        e = nmse(batch[u], singles[u])
+        print(f"utterance {u} (S = {batch[u].shape[1]}): batched vs alone nmse {e:.3e} max-abs {np.abs(batch[u] - singles[u]).max():.3e}")
+        assert e < 1e-4
+    # and the single-utterance path still works after a batch (buffers / graph keyed on the batch shape)
+    again = hostlib_full.diffusion(engine_f32, hostlib_full.rng(0), lat0, 80)
+    assert np.abs(again - g["mel"]).max() < TOL or nmse(again, g["mel"]) < 1e-4

@@ -152,7 +152,8 @@ def test_c_abi_exports_every_declared_symbol():
     for name in sorted(decl["tortoise_b200.h"] | decl["tortoise_host.h"] | decl["tortoise_b200_bench.h"]):
         assert hasattr(full, name), f"libtortoise_b200.so lacks {name}"
     host = ctypes.CDLL(os.path.join(os.path.dirname(pkg.LIB_PATH), "libtortoise_host.so"))
-    drivers = {"tts_host_autoregressive", "tts_host_diffusion", "tts_host_vocoder", "tts_host_latents"}
+    drivers = {"tts_host_autoregressive", "tts_host_diffusion", "tts_host_vocoder", "tts_host_latents",
+               "tts_host_diffusion_batch"}
     for name in sorted(decl["tortoise_host.h"] - drivers):
         assert hasattr(host, name), f"libtortoise_host.so lacks {name}"
 

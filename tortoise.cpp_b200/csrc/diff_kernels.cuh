@@ -304,7 +304,7 @@ static __global__ void __launch_bounds__(DA_THREADS) diff_attn_kernel(const floa
     const int qi = q0 + warp * 4 + i;
     if (qi < T) {
       const float inv = 1.0f / l[i];
-      const size_t off = (size_t(seq) * T + qi) * kDim + head * kHeadDim;
+      const size_t off = (size_t(seq) * Tstride + qi) * kDim + head * kHeadDim;
       const float v0 = o[i][0] * inv, v1 = o[i][1] * inv;
       const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
       out_hi[off + lane] = h0;

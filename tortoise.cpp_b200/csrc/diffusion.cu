@@ -37,7 +37,7 @@ struct DiffModel {
   __half *w_inp, *w_integ, *w_out;
   float *b_inp, *b_integ, *b_out, *out_gn_w, *out_gn_b;
   // work buffers
-  int capS = 0, capSteps = 0;
+  int capS = 0, capSteps = 0, capU = 0;  // capacities: frames per sequence, sampling steps, utterances per batch
   float *X = nullptr, *CW = nullptr, *CE = nullptr, *H1 = nullptr, *QKV = nullptr, *OUT = nullptr, *INP = nullptr;
   float *stats = nullptr, *x_dev = nullptr, *noise_dev = nullptr, *lat_dev = nullptr;
   __half *A16 = nullptr, *CAT16 = nullptr, *XIN16 = nullptr, *ATThi = nullptr, *ATTlo = nullptr;
@@ -49,8 +49,18 @@ struct DiffModel {
   cudaGraphExec_t step_graph = nullptr;
   int graph_S = -1;
   int graph_kernels = 0;           // kernel nodes of step_graph (what one replay launches)
+  int graph_U = 0;
   size_t noise_cap = 0;
-  int run_S = 0, run_steps = 0, run_i = -1;  // streaming sampler state
+  int run_S = 0, run_steps = 0, run_i = -1;  // streaming sampler state (run_S = common row stride = longest utterance)
+  // utterance batching: U utterances = 2 U sequences (2u cond, 2u + 1 uncond) of different lengths on one launch set
+  int run_U = 0;
+  std::vector<int> run_Su;            // frames per utterance
+  std::vector<long long> run_xoff;    // offset of utterance u in x_dev (its own [100][S_u] layout)
+  std::vector<long long> run_noff;    // offset of utterance u's noise blocks in noise_dev
+  int *d_Tseq = nullptr, *d_Sutt = nullptr;       // device: valid frames per sequence [2U] / per utterance [U]
+  long long *d_xoff = nullptr, *d_noff = nullptr; // device copies of run_xoff / run_noff
+  const int *tseq = nullptr;          // what the launch helpers pass as per-sequence lengths (null: all sequences full)
+  size_t x_cap = 0;
   double *gn_partial = nullptr;    // fused GroupNorm statistics written by the last GEMM epilogue
   const float *partial_src = nullptr;  // ... and the tensor they describe (null = stale)
   int partial_mtiles = 0;
@@ -190,32 +200,38 @@ static void grow(tts_ctx *c, T **p, size_t n) {
   TTS_CUDA_TRY(ctx_malloc(c, p, n * sizeof(T)));
 }
 
-static void ensure_buffers(tts_ctx *c, int S, int steps) {
+static void ensure_buffers(tts_ctx *c, int S, int steps, int U = 1) {
   DiffModel &m = *c->diff;
-  if (S > m.capS) {
-    const size_t s2 = size_t(2) * S;
+  if (S > m.capS || U > m.capU) {
+    S = std::max(S, m.capS);
+    U = std::max(U, m.capU);
+    const size_t nseq = size_t(2) * U, s2 = nseq * S;
     grow(c, &m.X, s2 * kDim);
     grow(c, &m.CW, s2 * kDim);
     grow(c, &m.CE, s2 * kDim);
     grow(c, &m.H1, s2 * kDim);
     grow(c, &m.QKV, s2 * 3072);
     grow(c, &m.OUT, s2 * 200);
-    grow(c, &m.INP, size_t(S) * kDim);
-    grow(c, &m.stats, size_t(2) * 32 * 2);
-    grow(c, &m.x_dev, size_t(100) * S);
+    grow(c, &m.INP, size_t(U) * S * kDim);
+    grow(c, &m.stats, nseq * 32 * 2);
     grow(c, &m.lat_dev, size_t(S) * kDim);
-    grow(c, &m.A16, size_t(2) * (S + 2) * kDim);
-    grow(c, &m.CAT16, size_t(2) * (S + 2) * 2048);
-    grow(c, &m.XIN16, size_t(S + 2) * 128);
+    grow(c, &m.A16, nseq * (S + 2) * kDim);
+    grow(c, &m.CAT16, nseq * (S + 2) * 2048);
+    grow(c, &m.XIN16, size_t(U) * (S + 2) * 128);
     grow(c, &m.ATThi, s2 * kDim);
     grow(c, &m.ATTlo, s2 * kDim);
     grow(c, &m.rpb, size_t(S) + 8);
     grow(c, &m.up_idx, size_t(S));
+    grow(c, &m.gn_partial, nseq * 32 * 64 * 2);
+    grow(c, &m.d_Tseq, nseq);
+    grow(c, &m.d_Sutt, size_t(U));
+    grow(c, &m.d_xoff, size_t(U));
+    grow(c, &m.d_noff, size_t(U));
     if (!m.d_step) TTS_CUDA_TRY(ctx_malloc(c, &m.d_step, 4));
-    if (!m.gn_partial) TTS_CUDA_TRY(ctx_malloc(c, &m.gn_partial, size_t(2) * 32 * 64 * 2 * sizeof(double)));
     m.partial_src = nullptr;  // buffers moved: no tensor has fused statistics
     if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; m.graph_S = -1; }
     m.capS = S;
+    m.capU = U;
     m.cond_L = m.cond_S = -1;
   }
   if (steps > m.capSteps) {
@@ -237,6 +253,7 @@ static void tg(tts_ctx *c, const Launcher &L, const __half *Ahi, const __half *A
   DiffModel &m = *c->diff;
   const int Tt = T > 0 ? T : M;
   TGemmArgs g{Ahi, Alo, Whi, Wlo, bias, C, nullptr, nullptr, M, N, K, lda, ldc, 0, epi, taps, 1, taps / 2, halo, Tt};
+  g.Tseq = T > 0 ? m.tseq : nullptr;
   // outputs that feed a GroupNorm (x, h1, code embedding): let the epilogue produce the statistics
   const bool gn_target = T > 0 && N == kDim && (C == m.X || C == m.CW || C == m.H1) && Tt <= 64 * T5_BM;
   if (gn_target) g.gn_partial = m.gn_partial;
@@ -256,9 +273,9 @@ static void gn(tts_ctx *c, const Launcher &L, const float *X, const float *w, co
   DiffModel &m = *c->diff;
   const bool fused = m.partial_src == X;
   if (out32 && out32 == m.partial_src) m.partial_src = nullptr;  // about to be overwritten
-  if (!fused) L(gn_stats_kernel, dim3(32, nseq), dim3(256), 0, X, m.stats, T);
+  if (!fused) L(gn_stats_kernel, dim3(32, nseq), dim3(256), 0, X, m.stats, T, m.tseq);
   L(gn_apply_kernel, dim3(T + 2, nseq), dim3(256), 0, X, (const float *)m.stats, w, b, ss, out16, out32, T, 1, kDim,
-    silu, (const int *)m.d_step, 16 * 2048, (const double *)(fused ? m.gn_partial : nullptr), m.partial_mtiles);
+    silu, (const int *)m.d_step, 16 * 2048, (const double *)(fused ? m.gn_partial : nullptr), m.partial_mtiles, m.tseq);
 }
 
 // ResBlock (main.cpp:3347-3480): x += conv3(silu((GN(h)w+b)(1+scale)+shift)),
@@ -278,18 +295,23 @@ static void attn_block(tts_ctx *c, const Launcher &L, const DAttn &a, float *x, 
   conv(c, L, m.A16, a.w_qkv, a.b_qkv, m.QKV, nseq, T, kDim, 3072, 1, 3072, E_BIAS);
   ensure_smem_attr(diff_attn_kernel, DA_SMEM);
   L(diff_attn_kernel, dim3((T + DA_Q - 1) / DA_Q, kHeads, nseq), dim3(DA_THREADS), DA_SMEM, (const float *)m.QKV,
-    (const float *)a.relbias, (const int *)m.rpb, m.ATThi, m.ATTlo, T);
+    (const float *)a.relbias, (const int *)m.rpb, m.ATThi, m.ATTlo, T, m.tseq);
   tg(c, L, m.ATThi, m.ATTlo, a.proj_hi, a.proj_lo, a.b_proj, x, nseq * T, kDim, kDim, kDim, kDim, E_BIAS_RESID,
      1, T, 0);  // per-sequence M tiles so the fused GroupNorm statistics stay per sequence
 }
 
 // timestep-invariant conditioning branch -> CE[0] (conditioned, stretched to S), CE[1]
 // (unconditioned broadcast).  main.cpp:3157-3328.
-static void prepare_conditioning(tts_ctx *c, const Launcher &L, const float *latents_host, int Lf, int S) {
+// Utterance batching: utterance u of a batch has its own Lf and S (<= Smax, the common row stride) and owns
+// sequences 2u / 2u + 1 of CE; rows [S, Smax) of its sequences are zero padding.
+static void prepare_conditioning(tts_ctx *c, const Launcher &L, const float *latents_host, int Lf, int S, int u = 0,
+                                 int Smax = 0) {
   DiffModel &m = *c->diff;
-  std::vector<int> rpb = tts_host::relative_position_table(S + 8);
+  if (Smax <= 0) Smax = S;
+  m.tseq = nullptr;  // the conditioning branch works on ONE sequence of Lf rows
+  std::vector<int> rpb = tts_host::relative_position_table(Smax + 8);
   std::vector<int> up = tts_host::upscale_index(Lf, S);
-  TTS_CUDA_TRY(cudaMemcpyAsync(m.rpb, rpb.data(), size_t(S + 8) * 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(m.rpb, rpb.data(), size_t(Smax + 8) * 4, cudaMemcpyHostToDevice, c->stream));
   TTS_CUDA_TRY(cudaMemcpyAsync(m.up_idx, up.data(), size_t(S) * 4, cudaMemcpyHostToDevice, c->stream));
   TTS_CUDA_TRY(cudaMemcpyAsync(m.lat_dev, latents_host, size_t(Lf) * kDim * 4, cudaMemcpyHostToDevice, c->stream));
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
@@ -299,8 +321,8 @@ static void prepare_conditioning(tts_ctx *c, const Launcher &L, const float *lat
   // code_norm, then * (1 + cond_latent[:1024]) + cond_latent[1024:]  (main.cpp:3293-3317)
   // (cond_latent is not a per-step table: d_step is 0 whenever the conditioning branch runs)
   gn(c, L, m.CW, m.code_norm_w, m.code_norm_b, m.cond_latent, nullptr, m.H1, 1, Lf, 0);
-  L(code_emb_kernel, dim3(S, 2), dim3(256), 0, (const float *)m.H1, (const int *)m.up_idx,
-    (const float *)m.uncond_emb, m.CE, S);
+  L(code_emb_kernel, dim3(Smax, 2), dim3(256), 0, (const float *)m.H1, (const int *)m.up_idx,
+    (const float *)m.uncond_emb, m.CE + size_t(2 * u) * Smax * kDim, Smax, S);
   m.cond_L = Lf;
   m.cond_S = S;
 }
@@ -324,15 +346,22 @@ static void prepare_time(tts_ctx *c, const Launcher &L, const std::vector<int> &
 
 // One denoiser evaluation on nseq sequences.  CW must hold the code embedding of each
 // sequence, x_dev the current x.  emb: this step's [16][2048] scale|shift table.
-static void run_denoiser(tts_ctx *c, const Launcher &L, int nseq, int S, const float *emb) {
+// Batched sampling: nseq = 2 U sequences with row stride S and per-sequence lengths d_Tseq (m.tseq), x of the
+// U utterances in x_dev at d_xoff; the input block runs once per utterance (d_Sutt).
+static void run_denoiser(tts_ctx *c, const Launcher &L, int nseq, int S, const float *emb, int U = 1) {
   DiffModel &m = *c->diff;
+  const int *tseq_all = m.tseq;
+  const bool batched = tseq_all != nullptr;
   for (int i = 0; i < 3; ++i) {
     res_block(c, L, m.res[i], m.CW, nseq, S, emb + size_t(i) * 2048);
     attn_block(c, L, m.attn[i], m.CW, nseq, S);
   }
-  L(xin_kernel, dim3(S + 2), dim3(128), 0, (const float *)m.x_dev, m.XIN16, S);
-  conv(c, L, m.XIN16, m.w_inp, m.b_inp, m.INP, 1, S, 128, kDim, 3, kDim, E_BIAS);
-  L(concat_kernel, dim3(S + 2, nseq), dim3(256), 0, (const float *)m.INP, (const float *)m.CW, m.CAT16, S);
+  L(xin_kernel, dim3(S + 2, U), dim3(128), 0, (const float *)m.x_dev, m.XIN16, S, (const int *)(batched ? m.d_Sutt : nullptr),
+    (const long long *)(batched ? m.d_xoff : nullptr));
+  m.tseq = batched ? m.d_Sutt : nullptr;  // the input block runs per UTTERANCE (cond and uncond share x)
+  conv(c, L, m.XIN16, m.w_inp, m.b_inp, m.INP, U, S, 128, kDim, 3, kDim, E_BIAS);
+  m.tseq = tseq_all;
+  L(concat_kernel, dim3(S + 2, nseq), dim3(256), 0, (const float *)m.INP, (const float *)m.CW, m.CAT16, S, m.tseq);
   conv(c, L, m.CAT16, m.w_integ, m.b_integ, m.X, nseq, S, 2048, kDim, 1, kDim, E_BIAS);
   for (int i = 0; i < 10; ++i) {
     res_block(c, L, m.res[3 + i], m.X, nseq, S, emb + size_t(3 + i) * 2048);
@@ -370,6 +399,13 @@ void diff_eps(tts_ctx *c, const float *latents, int Lf, const float *x, int S, i
   TTS_CUDA_TRY(cudaMemsetAsync(m.d_step, 0, 4, c->stream));
   prepare_conditioning(c, L, latents, Lf, S);
   prepare_time(c, L, {timestep});
+  if (m.x_cap < size_t(100) * S) {
+    if (m.x_dev) ctx_free(c, m.x_dev);
+    m.x_dev = nullptr;
+    TTS_CUDA_TRY(ctx_malloc(c, &m.x_dev, size_t(100) * S * 4));
+    m.x_cap = size_t(100) * S;
+    if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; m.graph_S = -1; }
+  }
   TTS_CUDA_TRY(cudaMemcpyAsync(m.x_dev, x, size_t(100) * S * 4, cudaMemcpyHostToDevice, c->stream));
   TTS_CUDA_TRY(cudaMemcpyAsync(m.CW, m.CE + (cond_free ? size_t(S) * kDim : 0), size_t(S) * kDim * 4,
                                cudaMemcpyDeviceToDevice, c->stream));
@@ -404,6 +440,15 @@ static int count_kernel_nodes(cudaGraph_t graph) {
   return k;
 }
 
+// Debug only (tortoise_b200_bench.h): copy one of the denoiser's activation buffers to the host
+void diff_debug_read(tts_ctx *c, int which, float *out, size_t n) {
+  if (!c->diff) throw ArgError("diffusion model not loaded");
+  DiffModel &m = *c->diff;
+  const float *src = which == 0 ? m.CW : which == 1 ? m.X : which == 2 ? m.OUT : which == 3 ? m.INP : which == 4 ? m.QKV : which == 6 ? m.CE : which == 7 ? reinterpret_cast<const float *>(m.ATThi) : m.H1;
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  TTS_CUDA_TRY(cudaMemcpy(out, src, n * 4, cudaMemcpyDeviceToHost));
+}
+
 // Measurement only (tortoise_b200_bench.h): the denoiser's 3-tap convolution -- the GEMM shape the diffusion
 // stage spends most of its time in -- `iters` back-to-back launches on the model's own weights between two
 // CUDA events.  M = 2 S rows (cond + uncond), N = K = 1024.
@@ -429,67 +474,112 @@ void diff_bench_conv3(tts_ctx *c, int S, int iters, float *ms, double *flop) {
   c->launches += iters + 3;
 }
 
-void diff_begin(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, const float *x0) {
-  check_sizes(c, Lf, S);
+// Streaming form of the sampling loop for a BATCH of U utterances (U = 1: the reference's loop): begin
+// (conditioning per utterance, schedule, x0) / step (upload every utterance's noise block, enqueue the captured
+// step graph -- asynchronous) / end (read the mels).  The host draws the noise of step i + 1 from each
+// utterance's own RNG stream while the GPU runs step i.  Utterance u owns sequences 2u (cond) and 2u + 1
+// (uncond) of every activation buffer; all sequences share the row stride Smax = max S_u and carry their own
+// length, so one launch set serves utterances of different lengths (BASELINE configs[4]) and the GEMMs see
+// M = 2 * sum(S_u) rows instead of 2 S.
+void diff_begin_batch(tts_ctx *c, int U, const float *const *latents, const int32_t *Lf, const int32_t *S, int n_steps,
+                      const float *const *x0) {
+  if (U < 1 || U > 64) throw ArgError("batch of 1..64 utterances", TTS_ELIMIT);
   if (n_steps < 1 || n_steps > 4000) throw ArgError("bad n_steps");
+  int Smax = 0;
+  for (int u = 0; u < U; ++u) {
+    check_sizes(c, Lf[u], S[u]);
+    Smax = std::max(Smax, int(S[u]));
+  }
   DiffModel &m = *c->diff;
-  ensure_buffers(c, S, n_steps);
+  ensure_buffers(c, Smax, n_steps, U);
+  Smax = U > 1 ? Smax : S[0];
   Launcher L{c->stream, c->use_pdl, &c->launches};
-  const size_t nx = size_t(100) * S;
   TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
   TTS_CUDA_TRY(cudaMemsetAsync(m.d_step, 0, 4, c->stream));  // conditioning branch must see step 0
   const std::vector<tts_host::DdpmStep> sched = tts_host::ddpm_schedule(n_steps);
   std::vector<DdpmCoef> coefs(n_steps);
   std::vector<int> timesteps(n_steps);
   for (int i = 0; i < n_steps; ++i) {
-    const auto &s = sched[i];
-    coefs[i] = DdpmCoef{s.cfk, s.sqrt_recip, s.sqrt_recipm1, s.coef1, s.coef2, s.min_log, s.max_log, s.last};
-    timesteps[i] = s.timestep;
+    const auto &sd = sched[i];
+    coefs[i] = DdpmCoef{sd.cfk, sd.sqrt_recip, sd.sqrt_recipm1, sd.coef1, sd.coef2, sd.min_log, sd.max_log, sd.last};
+    timesteps[i] = sd.timestep;
   }
   TTS_CUDA_TRY(cudaMemcpyAsync(m.coefs, coefs.data(), coefs.size() * sizeof(DdpmCoef), cudaMemcpyHostToDevice, c->stream));
-  prepare_conditioning(c, L, latents, Lf, S);
+  m.run_U = U;
+  m.run_Su.assign(S, S + U);
+  m.run_xoff.assign(U, 0);
+  m.run_noff.assign(U, 0);
+  size_t nx_total = 0;
+  for (int u = 0; u < U; ++u) {
+    m.run_xoff[u] = (long long)nx_total;
+    m.run_noff[u] = (long long)(nx_total * size_t(n_steps + 1));
+    nx_total += size_t(100) * S[u];
+  }
+  if (U > 1) TTS_CUDA_TRY(cudaMemsetAsync(m.CE, 0, size_t(2) * U * Smax * kDim * 4, c->stream));
+  for (int u = 0; u < U; ++u) prepare_conditioning(c, L, latents[u], Lf[u], S[u], u, Smax);
   prepare_time(c, L, timesteps);
-  // noise: block 0 = initial x, block i+1 = the draw of step i (always drawn, used unless last)
-  // (the graph embeds this pointer: reallocation drops the captured graph)
-  if (m.noise_cap < size_t(n_steps + 1) * nx) {
+  // noise: per utterance, block 0 = initial x, block i + 1 = the draw of step i (always drawn, used unless last)
+  // (the graph embeds these pointers: reallocation drops the captured graph)
+  if (m.noise_cap < size_t(n_steps + 1) * nx_total || m.x_cap < nx_total) {
     if (m.noise_dev) ctx_free(c, m.noise_dev);
-    m.noise_dev = nullptr;
-    TTS_CUDA_TRY(ctx_malloc(c, &m.noise_dev, size_t(n_steps + 1) * nx * 4));
-    m.noise_cap = size_t(n_steps + 1) * nx;
+    if (m.x_dev) ctx_free(c, m.x_dev);
+    m.noise_dev = m.x_dev = nullptr;
+    TTS_CUDA_TRY(ctx_malloc(c, &m.noise_dev, size_t(n_steps + 1) * nx_total * 4));
+    TTS_CUDA_TRY(ctx_malloc(c, &m.x_dev, nx_total * 4));
+    m.noise_cap = size_t(n_steps + 1) * nx_total;
+    m.x_cap = nx_total;
     if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; m.graph_S = -1; }
   }
-  float *hp = pin(c, size_t(n_steps + 1) * nx * 4);
-  memcpy(hp, x0, nx * 4);
-  TTS_CUDA_TRY(cudaMemcpyAsync(m.noise_dev, hp, nx * 4, cudaMemcpyHostToDevice, c->stream));
-  TTS_CUDA_TRY(cudaMemcpyAsync(m.x_dev, m.noise_dev, nx * 4, cudaMemcpyDeviceToDevice, c->stream));
+  float *hp = pin(c, size_t(n_steps + 1) * nx_total * 4);
+  for (int u = 0; u < U; ++u) {
+    const size_t nx = size_t(100) * S[u];
+    memcpy(hp + m.run_noff[u], x0[u], nx * 4);
+    TTS_CUDA_TRY(cudaMemcpyAsync(m.noise_dev + m.run_noff[u], hp + m.run_noff[u], nx * 4, cudaMemcpyHostToDevice, c->stream));
+    TTS_CUDA_TRY(cudaMemcpyAsync(m.x_dev + m.run_xoff[u], m.noise_dev + m.run_noff[u], nx * 4, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (U > 1) {  // per-sequence / per-utterance lengths and offsets the batched kernels read
+    std::vector<int> tseq(2 * U);
+    for (int u = 0; u < U; ++u) tseq[2 * u] = tseq[2 * u + 1] = S[u];
+    TTS_CUDA_TRY(cudaMemcpyAsync(m.d_Tseq, tseq.data(), tseq.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    TTS_CUDA_TRY(cudaMemcpyAsync(m.d_Sutt, m.run_Su.data(), size_t(U) * 4, cudaMemcpyHostToDevice, c->stream));
+    TTS_CUDA_TRY(cudaMemcpyAsync(m.d_xoff, m.run_xoff.data(), size_t(U) * 8, cudaMemcpyHostToDevice, c->stream));
+    TTS_CUDA_TRY(cudaMemcpyAsync(m.d_noff, m.run_noff.data(), size_t(U) * 8, cudaMemcpyHostToDevice, c->stream));
+    TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));  // host vector goes out of scope
+  }
   TTS_CUDA_TRY(cudaMemsetAsync(m.d_step, 0, 4, c->stream));
-  m.run_S = S;
+  m.run_S = Smax;
   m.run_steps = n_steps;
   m.run_i = 0;
 }
 
-void diff_step(tts_ctx *c, const float *noise_block) {
+void diff_step_batch(tts_ctx *c, const float *const *noise_blocks) {
   if (!c->diff || c->diff->run_i < 0 || c->diff->run_i >= c->diff->run_steps) throw ArgError("tts_diffusion_step out of sequence");
   DiffModel &m = *c->diff;
-  const int S = m.run_S, i = m.run_i;
-  const size_t nx = size_t(100) * S;
+  const int S = m.run_S, i = m.run_i, U = m.run_U;
   Launcher L{c->stream, c->use_pdl, &c->launches};
-  float *hp = m.h_pin + size_t(i + 1) * nx;  // pinned slot of this block (stable until the copy ran)
-  memcpy(hp, noise_block, nx * 4);
-  TTS_CUDA_TRY(cudaMemcpyAsync(m.noise_dev + size_t(i + 1) * nx, hp, nx * 4, cudaMemcpyHostToDevice, c->stream));
-  // One sampling step = memcpy(code embedding) + ~165 kernels + DDPM update + step counter.
+  for (int u = 0; u < U; ++u) {
+    const size_t nx = size_t(100) * m.run_Su[u];
+    float *hp = m.h_pin + m.run_noff[u] + size_t(i + 1) * nx;  // pinned slot of this block (stable until the copy ran)
+    memcpy(hp, noise_blocks[u], nx * 4);
+    TTS_CUDA_TRY(cudaMemcpyAsync(m.noise_dev + m.run_noff[u] + size_t(i + 1) * nx, hp, nx * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  // One sampling step = memcpy(code embedding) + ~125 kernels + DDPM update + step counter.
   // Everything that varies per step is read through the device-side counter d_step, so the
   // step is captured once into a CUDA graph and replayed n_steps times.
   auto enqueue_step = [&](const Launcher &LL) {
-    TTS_CUDA_TRY(cudaMemcpyAsync(m.CW, m.CE, size_t(2) * S * kDim * 4, cudaMemcpyDeviceToDevice, c->stream));
+    TTS_CUDA_TRY(cudaMemcpyAsync(m.CW, m.CE, size_t(2) * U * S * kDim * 4, cudaMemcpyDeviceToDevice, c->stream));
     m.partial_src = nullptr;  // CW was overwritten by a copy: its fused statistics are stale
-    run_denoiser(c, LL, 2, S, m.EMB);
-    LL(ddpm_step_kernel, dim3(std::min(148, int((nx + 255) / 256))), dim3(256), 0, m.x_dev, (const float *)m.OUT,
-       (const float *)m.noise_dev, (const DdpmCoef *)m.coefs, (const int *)m.d_step, S);
+    m.tseq = U > 1 ? m.d_Tseq : nullptr;
+    run_denoiser(c, LL, 2 * U, S, m.EMB, U);
+    m.tseq = nullptr;
+    const size_t nx_max = size_t(100) * S;
+    LL(ddpm_step_kernel, dim3(std::min(148, int((nx_max + 255) / 256)), U), dim3(256), 0, m.x_dev, (const float *)m.OUT,
+       (const float *)m.noise_dev, (const DdpmCoef *)m.coefs, (const int *)m.d_step, S, (const int *)(U > 1 ? m.d_Sutt : nullptr),
+       (const long long *)(U > 1 ? m.d_xoff : nullptr), (const long long *)(U > 1 ? m.d_noff : nullptr));
     LL(step_inc_kernel, dim3(1), dim3(32), 0, m.d_step);
   };
   if (c->use_graph) {
-    if (!m.step_graph || m.graph_S != S) {
+    if (!m.step_graph || m.graph_S != S || m.graph_U != U) {
       if (m.step_graph) cudaGraphExecDestroy(m.step_graph);
       m.step_graph = nullptr;
       int64_t dummy = 0;
@@ -510,6 +600,7 @@ void diff_step(tts_ctx *c, const float *noise_block) {
       TTS_CUDA_TRY(cudaGraphInstantiate(&m.step_graph, graph, 0));
       cudaGraphDestroy(graph);
       m.graph_S = S;
+      m.graph_U = U;
     }
     TTS_CUDA_TRY(cudaGraphLaunch(m.step_graph, c->stream));
     c->launches += m.graph_kernels;
@@ -519,20 +610,28 @@ void diff_step(tts_ctx *c, const float *noise_block) {
   m.run_i += 1;
 }
 
-void diff_end(tts_ctx *c, float *mel) {
+void diff_end_batch(tts_ctx *c, float *const *mel) {
   if (!c->diff || c->diff->run_i != c->diff->run_steps || c->diff->run_steps <= 0) throw ArgError("tts_diffusion_end before all steps ran");
   DiffModel &m = *c->diff;
-  const size_t nx = size_t(100) * m.run_S;
-  float *h = m.h_pin;  // slot 0 (x0 copy long done)
-  TTS_CUDA_TRY(cudaMemcpyAsync(h, m.x_dev, nx * 4, cudaMemcpyDeviceToHost, c->stream));
+  size_t nx_total = 0;
+  for (int u = 0; u < m.run_U; ++u) nx_total += size_t(100) * m.run_Su[u];
+  float *h = m.h_pin;  // the x0 slots are long consumed
+  TTS_CUDA_TRY(cudaMemcpyAsync(h, m.x_dev, nx_total * 4, cudaMemcpyDeviceToHost, c->stream));
   TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   c->total_ms += c->last_ms;
-  memcpy(mel, h, nx * 4);
+  for (int u = 0; u < m.run_U; ++u) memcpy(mel[u], h + m.run_xoff[u], size_t(100) * m.run_Su[u] * 4);
   m.run_i = -1;
   m.run_steps = 0;
 }
+
+void diff_begin(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, const float *x0) {
+  const int32_t l = Lf, sv = S;
+  diff_begin_batch(c, 1, &latents, &l, &sv, n_steps, &x0);
+}
+void diff_step(tts_ctx *c, const float *noise_block) { diff_step_batch(c, &noise_block); }
+void diff_end(tts_ctx *c, float *mel) { diff_end_batch(c, &mel); }
 
 void diff_sample(tts_ctx *c, const float *latents, int Lf, int S, int n_steps, const float *noise, float *mel) {
   check_sizes(c, Lf, S);

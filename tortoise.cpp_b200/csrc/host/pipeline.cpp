@@ -168,6 +168,31 @@ int tts_host_diffusion(struct tts_ctx *ctx, tts_rng *rng, const float *latents, 
   return tts_diffusion_end(ctx, mel_out);
 }
 
+int tts_host_diffusion_batch(struct tts_ctx *ctx, tts_rng *const *rngs, int U, const float *const *latents, const int32_t *L,
+                             int n_steps, float *const *mel_out, int32_t *S_out) {
+  if (!ctx || !rngs || !latents || !L || !mel_out || U < 1 || n_steps < 1) return TTS_EINVAL;
+  std::vector<int32_t> S(U);
+  std::vector<std::vector<float>> blk(U);
+  std::vector<const float *> ptr(U);
+  for (int u = 0; u < U; ++u) {
+    if (!rngs[u] || !latents[u] || !mel_out[u] || L[u] < 1) return TTS_EINVAL;
+    S[u] = L[u] * 4 * 24000 / 22050;  // main.cpp:5616-5617 (integer arithmetic)
+    if (S_out) S_out[u] = S[u];
+    blk[u].resize(size_t(100) * S[u]);
+    for (float &v : blk[u]) v = rngs[u]->r.normal(rngs[u]->r.generator);  // initial x (main.cpp:5638)
+    ptr[u] = blk[u].data();
+  }
+  int rc = tts_diffusion_begin_batch(ctx, U, latents, L, S.data(), n_steps, ptr.data());
+  if (rc != TTS_OK) return rc;
+  for (int s = 0; s < n_steps; ++s) {
+    for (int u = 0; u < U; ++u)
+      for (float &v : blk[u]) v = rngs[u]->r.normal(rngs[u]->r.generator);  // one block per step, last included (main.cpp:6020)
+    rc = tts_diffusion_step_batch(ctx, ptr.data());
+    if (rc != TTS_OK) return rc;
+  }
+  return tts_diffusion_end_batch(ctx, mel_out);
+}
+
 int tts_host_vocoder(struct tts_ctx *ctx, tts_rng *rng, const float *mel, int S, float *audio_out) {
   if (!ctx || !rng || !mel || !audio_out || S < 1) return TTS_EINVAL;
   std::vector<float> noise(size_t(S + 10) * 64);  // main.cpp:6057

@@ -145,6 +145,18 @@ int tts_diffusion_step(tts_ctx *c, const float *noise_block) {
 int tts_diffusion_end(tts_ctx *c, float *mel) {
   TTS_API_BODY(c, if (!mel) throw tts::ArgError("null argument"); tts::diff_end(c, mel))
 }
+int tts_diffusion_begin_batch(tts_ctx *c, int32_t U, const float *const *latents, const int32_t *L, const int32_t *S,
+                              int32_t n_steps, const float *const *x0) {
+  TTS_API_BODY(c, if (!latents || !L || !S || !x0 || U < 1) throw tts::ArgError("bad argument");
+               for (int u = 0; u < U; ++u) if (!latents[u] || !x0[u]) throw tts::ArgError("null argument");
+               tts::diff_begin_batch(c, U, latents, L, S, n_steps, x0))
+}
+int tts_diffusion_step_batch(tts_ctx *c, const float *const *noise_blocks) {
+  TTS_API_BODY(c, if (!noise_blocks) throw tts::ArgError("null argument"); tts::diff_step_batch(c, noise_blocks))
+}
+int tts_diffusion_end_batch(tts_ctx *c, float *const *mel) {
+  TTS_API_BODY(c, if (!mel) throw tts::ArgError("null argument"); tts::diff_end_batch(c, mel))
+}
 int tts_vocoder(tts_ctx *c, const float *mel, int32_t S, const float *noise, float *audio) {
   TTS_API_BODY(c, if (!mel || !noise || !audio) throw tts::ArgError("null argument"); tts::voc_run(c, mel, S, noise, audio))
 }
@@ -157,6 +169,9 @@ int tts_bench_gemv(tts_ctx *c, int32_t op, int32_t B, int32_t iters, float *ms, 
   TTS_API_BODY(c, if (!ms || !bytes || iters < 1) throw tts::ArgError("bad argument"); tts::ar_bench_gemv(c, op, B, iters, ms, bytes))
 }
 
+int tts_debug_diffusion_buffer(tts_ctx *c, int32_t which, float *out, int64_t n) {
+  TTS_API_BODY(c, if (!out || n < 1) throw tts::ArgError("bad argument"); tts::diff_debug_read(c, which, out, size_t(n)))
+}
 int tts_bench_conv3(tts_ctx *c, int32_t S, int32_t iters, float *ms, double *flop) {
   TTS_API_BODY(c, if (!ms || !flop) throw tts::ArgError("bad argument"); tts::diff_bench_conv3(c, S, iters, ms, flop))
 }

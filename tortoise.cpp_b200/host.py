@@ -54,6 +54,7 @@ class HostLib:
                                                     f32p, i32p]
             lib.tts_host_diffusion.argtypes = [vp, vp, f32p, i32, i32, f32p, i32p]
             lib.tts_host_latents.argtypes = [vp, i32p, i32, f32p, i32p, f32p, i32p]
+            lib.tts_host_diffusion_batch.argtypes = [vp, P(vp), i32, P(f32p), i32p, i32, P(f32p), i32p]
             lib.tts_host_vocoder.argtypes = [vp, vp, f32p, i32, f32p]
         self.lib = lib
         self.full = full
@@ -210,6 +211,24 @@ class HostLib:
             raise RuntimeError(f"tts_host_diffusion failed ({rc}): {engine.lib.tts_last_error(engine.h).decode()}")
         assert s_out.value == S
         return mel
+
+    def diffusion_batch(self, engine, rngs, latents_list, n_steps=80):
+        """U utterances on one launch set (utterance batching); returns a list of mels [100][S_u]"""
+        assert self.full
+        U = len(latents_list)
+        lats = [np.ascontiguousarray(l, dtype=np.float32) for l in latents_list]
+        L = np.array([l.shape[0] for l in lats], dtype=np.int32)
+        mels = [np.empty((100, int(l) * 4 * 24000 // 22050), dtype=np.float32) for l in L]
+        f32p = C.POINTER(C.c_float)
+        lat_p = (f32p * U)(*[l.ctypes.data_as(f32p) for l in lats])
+        mel_p = (f32p * U)(*[m.ctypes.data_as(f32p) for m in mels])
+        rng_p = (C.c_void_p * U)(*[r.h for r in rngs])
+        s_out = np.empty(U, dtype=np.int32)
+        rc = self.lib.tts_host_diffusion_batch(engine.h, rng_p, U, lat_p, L.ctypes.data_as(C.POINTER(C.c_int32)), n_steps, mel_p,
+                                               s_out.ctypes.data_as(C.POINTER(C.c_int32)))
+        if rc != 0:
+            raise RuntimeError(f"tts_host_diffusion_batch failed ({rc}): {engine.lib.tts_last_error(engine.h).decode()}")
+        return mels
 
     def vocoder(self, engine, rng, mel):
         assert self.full
