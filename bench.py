@@ -18,7 +18,8 @@ forced to round(1.5 * chars) so the work does not depend on when the
             (tts_gather_select), then ONLY the winner's owner runs latent pass + 200-step diffusion +
             vocoder.  `value` is the RTF of the rendered utterance (flat in N by construction: one
             utterance is rendered whatever N is); what scales with N is `ar_mel_tokens_per_s`.
-  --config C5 (any N): configs[4], 256 utterances of 20-300 chars sharded u mod N, per-stage RTF.
+  --config C5 (any N): configs[4], 256 utterances of 20-300 chars sharded u mod N, --c5-batch U utterances per step
+    (AR per utterance, one utterance-batched diffusion per step, vocoder per utterance), per-stage RTF.
 
   value : audio-s / device time (CUDA events around every stage call), max over ranks
   e2e   : audio-s / wall time of the host-driven pipeline through the C-ABI with HOST buffers
@@ -69,7 +70,7 @@ def workload(name: str, world: int) -> dict:
                                                                 "best-candidate select, 50-char prompt"),
         "C4": dict(prompt=PROMPT_C4, cand=8, steps=200, label="configs[3]: 64 candidates at 8 GPUs = 8 candidates per GPU, 200-char prompt, "
                                                                 "NCCL gather of (score, length), winner-only latent pass + diffusion + vocoder"),
-        "C5": dict(prompt=None, cand=1, steps=80, label="configs[4]: 256 utterances, 20-300 chars, sharded u mod N, 1 candidate"),
+        "C5": dict(prompt=None, cand=1, steps=80, label="configs[4]: 256 utterances, 20-300 chars, sharded u mod N, 1 candidate, diffusion utterance-batched"),
     }[name]
     w = dict(w, name=name)
     w["codes"] = int(os.environ.get("TTS_BENCH_CODES", str(int(1.5 * len(w["prompt"]) + 0.5) if w["prompt"] else 0)))
@@ -351,6 +352,7 @@ def main():
     ap.add_argument("--config", default=os.environ.get("TTS_BENCH_CONFIG", "auto"), choices=["auto", "C2", "C3", "C4", "C5"])
     ap.add_argument("--ref-sample", default="full", choices=["full", "bounded"],
                     help="reference arm at configs[1]: one full utterance (default) or the bounded, extrapolated sample")
+    ap.add_argument("--c5-batch", type=int, default=8, help="configs[4]: utterances per step (one batched diffusion per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs[2] measurement at N = 1")
     args = ap.parse_args()
@@ -386,15 +388,46 @@ def main():
         group = run.pkg.Group([eng], rank=rank, world=world, unique_id=ids[0])
 
     prompts = c5_prompts() if cfg_name == "C5" else None
-    my_utts = list(range(rank, 256, world)) if cfg_name == "C5" else None
+    U5 = max(1, args.c5_batch)
+    if cfg_name == "C5":  # this rank's share (u mod N), sorted by length so that a batch pads little
+        my_utts = sorted(range(rank, 256, world), key=lambda u: len(prompts[u]))
+        n_batches = (len(my_utts) + U5 - 1) // U5
+
+    def one_batch(k, seed):
+        """configs[4]: one step = U utterances of this rank: AR one by one (1 candidate each), ONE batched diffusion
+        (U utterances of different lengths on one launch set per step), vocoder one by one"""
+        b = (k * 7) % n_batches  # walk the length buckets rather than only the shortest ones
+        utts = my_utts[b * U5:(b + 1) * U5]
+        out = dict(ar_wall=0.0, ar_dev_ms=0.0, tokens=0, audio_s=0.0, diff_ms=0.0, voc_ms=0.0, h2d=0, d2h=0, gather_ms=0.0, owner=rank)
+        lats, rngs, meta = [], [], []
+        for j, u in enumerate(utts):
+            tokens = run.tokens(prompts[u])
+            codes = min(500 - 1, int(1.5 * len(prompts[u]) + 0.5))
+            a = run.ar(tokens, 1, codes, seed * 1000 + j, skip_latents=False)
+            out["ar_wall"] += a["wall"]
+            out["ar_dev_ms"] += a["dev_ms"]
+            out["tokens"] += a["steps"]
+            lats.append(a["lat"][0, :int(a["nlat"][0])])
+            rngs.append(a["rng"])
+            meta.append((len(tokens), a["steps"]))
+        d0 = eng.device_ms_total
+        mels = hl.diffusion_batch(eng, rngs, lats, w["steps"])
+        out["diff_ms"] = eng.device_ms_total - d0
+        for j, mel in enumerate(mels):
+            audio = hl.vocoder(eng, rngs[j], mel)
+            out["voc_ms"] += eng.last_stage_ms
+            out["audio_s"] += audio.size / 24000.0
+            hb, db = io_bytes(meta[j][0], 1, meta[j][1], lats[j].shape[0], mel.shape[1], w["steps"], audio.size, 1)
+            out["h2d"] += hb
+            out["d2h"] += db
+        out["utterances"] = len(utts)
+        return out
 
     def one_utterance(k, seed):
         """one step of the workload on this rank -> dict of times / sizes"""
         if cfg_name == "C5":
-            prompt = prompts[my_utts[k % len(my_utts)]]
-            codes = min(500 - 1, int(1.5 * len(prompt) + 0.5))
-        else:
-            prompt, codes = w["prompt"], w["codes"]
+            return one_batch(k, seed)
+        prompt, codes = w["prompt"], w["codes"]
         tokens = run.tokens(prompt)
         multi = world > 1 and cfg_name == "C4"
         a = run.ar(tokens, B, codes, seed, skip_latents=multi or B > 1)
@@ -455,7 +488,11 @@ def main():
         wall, dev_s, ar_wall, ar_dev_ms = mx[0].item(), mx[1].item(), mx[4].item(), mx[5].item()
         audio_total, tok_total = sm[2].item(), sm[3].item()
         diff_ms, voc_ms = sm[6].item(), sm[7].item()  # only the winner's owner has them
-        h2d, d2h, launches, gather_ms = int(mx[8].item()), int(mx[9].item()), int(sm[10].item()), mx[11].item()
+        mn = stats.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        # the gather's wall time on a rank that arrives early is mostly the wait for its peers (the previous step's
+        # owner is still rendering); the LAST rank to arrive sees the collective itself: min over ranks
+        h2d, d2h, launches, gather_ms = int(mx[8].item()), int(mx[9].item()), int(sm[10].item()), mn[11].item()
     else:
         audio_total, tok_total, ar_wall, ar_dev_ms = acc["audio_s"], float(acc["tokens"]), acc["ar_wall"], acc["ar_dev_ms"]
         diff_ms, voc_ms, gather_ms = acc["diff_ms"], acc["voc_ms"], 0.0
@@ -503,6 +540,13 @@ def main():
                             "us_per_launch": g_ms * 1e3, "flop_per_launch": g_flop,
                             "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({peak_kind})"},
     }
+    if cfg_name == "C5":
+        line["config"]["utterances_per_step"] = U5
+        line["config"]["batching"] = ("a step = U utterances of one length bucket on each rank: AR one utterance at a time, ONE "
+                                      "utterance-batched diffusion (2U sequences per launch set), vocoder one at a time")
+        line["stage_rtf"] = {"ar": audio_total / max(ar_dev_ms / 1e3, 1e-9), "diffusion": audio_total / max(diff_ms / 1e3, 1e-9),
+                             "vocoder": audio_total / max(voc_ms / 1e3, 1e-9),
+                             "note": "audio seconds / device seconds of that stage (sums over ranks for diffusion / vocoder at N > 1)"}
     if cfg_name == "C2" and world == 1 and not args.no_extra:
         line["c3"] = measure_c3(run, max(1, min(args.steps, 3)))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
