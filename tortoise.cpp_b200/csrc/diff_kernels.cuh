@@ -198,119 +198,197 @@ static __global__ void silu_split_kernel(const float *in, __half *hi, __half *lo
 
 // Self-attention with T5-style relative position bias (main.cpp:3547-3596):
 //   w_ij = softmax_j( q_i.k_j / 8 + 8 * relbias[bucket(i, j)][head] ),  out_i = sum_j w_ij v_j
-// QKV [nseq][T][3072] f32 with head h owning channels [192h, 192h+192): q | k | v.
+// QKV16 [nseq][T][3072] f16 with head h owning channels [192h, 192h+192): q | k | v.
 // bucket(i, j) = (j > i ? 16 : 0) + rpb[|j - i|] (main.cpp:4722-4749, table from the host).
 // Output as split-f16 planes [nseq*T][1024] (operand of the F32 proj_out matmul).
-// grid (ceil(T / DA_Q), 16, nseq) x DA_THREADS: 8 warps x 4 queries, keys staged in tiles of 64.
-// (32 queries per block instead of 16: every block re-reads the K and V of its head from L2 --
-// 98 KB at T = 191 -- so the block count per head IS the L2 traffic: 37.6 -> 18.8 MB per call.)
-constexpr int DA_WARPS = 8, DA_THREADS = DA_WARPS * 32, DA_Q = DA_WARPS * 4, DA_TK = 64, DA_LDK = kHeadDim + 4;
-constexpr size_t DA_SMEM = (size_t(2) * DA_TK * DA_LDK + size_t(DA_Q) * kHeadDim + size_t(DA_WARPS) * 4 * DA_TK + 32) * sizeof(float);
-static __global__ void __launch_bounds__(DA_THREADS) diff_attn_kernel(const float *QKV, const float *relbias, const int *rpb,
+// Flash-style: a block owns 16 NW queries of one (sequence, head), walks the keys in tiles of 64 (K and V tiles
+// double-buffered with cp.async), S = Q K^T and O += P V on mma.sync m16n8k16 (f16 operands, f32 accumulators),
+// online softmax in f32 on the accumulator fragments, P goes from the S accumulators straight into the A fragments
+// of the second product.  QKV16 is the f16 copy of conv1(GN(x)) the QKV GEMM's epilogue writes ([row][3072], head h
+// at columns 192 h: q | k | v); the relative-position bias of the block's (query, key) distances is tabulated once
+// per block (T + 16 NW - 1 entries).  exp is exp2 with log2(e) folded into the scale and the table.
+// Why mma.sync and not tcgen05 here: per (head, sequence) the products are 64-wide in K (head dim) with a softmax
+// between them -- an accumulator round trip TMEM -> registers -> shared per key tile -- and at S = 191 (BASELINE
+// configs[1]) the whole call is 0.6 GFLOP.  The f32 SIMT kernel this replaces (round 1) took 12 us per call at
+// S = 191 and ~0.55 ms at S = 1306: the sampling step went 1517 -> 1125 us (S = 191) and ~12 -> 4.9 ms (S = 1306).
+constexpr int TA_BK = 64, TA_LD = kHeadDim + 8;  // 72 halves per row: ldmatrix rows fall on distinct banks
+template <int NW>
+constexpr size_t ta_smem_bytes(int T) {
+  return size_t(16 * NW + 4 * TA_BK) * TA_LD * sizeof(__half) + size_t(T + 16 * NW) * sizeof(float) + 32 * sizeof(float);
+}
+__device__ __forceinline__ void ta_cp16(void *dst, const void *src, bool valid) {
+  const int n = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void ta_ldm4(uint32_t (&r)[4], const void *p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ta_ldm4_t(uint32_t (&r)[4], const void *p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ta_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t ta_pack(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// grid (ceil(T / (16 NW)), 16 heads, nseq) x 32 NW
+template <int NW>
+static __global__ void __launch_bounds__(NW * 32) diff_attn_tc_kernel(const __half *QKV16, const float *relbias, const int *rpb,
                                                                __half *out_hi, __half *out_lo, int Tstride, const int *Tseq) {
-  constexpr int TK = DA_TK, LDK = DA_LDK;
-  extern __shared__ __align__(16) float da_smem[];
-  float (*Ks)[LDK] = reinterpret_cast<float (*)[LDK]>(da_smem);
-  float (*Vs)[LDK] = reinterpret_cast<float (*)[LDK]>(da_smem + TK * LDK);
-  float (*Qs)[kHeadDim] = reinterpret_cast<float (*)[kHeadDim]>(da_smem + 2 * TK * LDK);
-  float (*Ps)[4][TK] = reinterpret_cast<float (*)[4][TK]>(da_smem + 2 * TK * LDK + DA_Q * kHeadDim);
-  float *bias_s = da_smem + 2 * TK * LDK + DA_Q * kHeadDim + DA_WARPS * 4 * TK;
+  constexpr int BQ = 16 * NW, NT = NW * 32, LD = TA_LD;
+  constexpr float kLog2e = 1.4426950408889634f;
+  extern __shared__ __align__(16) unsigned char ta_raw[];
+  __half (*Qs)[LD] = reinterpret_cast<__half (*)[LD]>(ta_raw);
+  __half (*Ks)[TA_BK][LD] = reinterpret_cast<__half (*)[TA_BK][LD]>(ta_raw + size_t(BQ) * LD * 2);
+  __half (*Vs)[TA_BK][LD] = reinterpret_cast<__half (*)[TA_BK][LD]>(ta_raw + size_t(BQ + 2 * TA_BK) * LD * 2);
+  float *bias_s = reinterpret_cast<float *>(ta_raw + size_t(BQ + 4 * TA_BK) * LD * 2);
+  float *bt = bias_s + 32;
   pdl_launch_dependents();
   pdl_wait();
-  const int t = threadIdx.x, warp = t / 32, lane = t % 32;
-  const int head = blockIdx.y, seq = blockIdx.z;
-  const int q0 = blockIdx.x * DA_Q;
-  const int T = Tseq ? Tseq[seq] : Tstride;  // this sequence's own length (keys / queries past it are padding)
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32, g = lane >> 2, t4 = lane & 3;
+  const int head = blockIdx.y, seq = blockIdx.z, q0 = blockIdx.x * BQ;
+  const int T = Tseq ? Tseq[seq] : Tstride;  // this sequence's own length (rows past it are padding)
   if (q0 >= T) return;
-  const float *base = QKV + size_t(seq) * Tstride * 3072 + head * 192;
-  if (t < 32) bias_s[t] = 8.0f * relbias[t * 16 + head];
-  for (int i = t; i < DA_Q * kHeadDim; i += DA_THREADS) {
-    const int r = i / kHeadDim, d = i % kHeadDim;
-    const int qi = q0 + r;
-    Qs[r][d] = qi < T ? base[size_t(qi) * 3072 + d] : 0.f;
-  }
-  float m[4], l[4], o[4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    m[i] = -INFINITY;
-    l[i] = 0.f;
-    o[i][0] = o[i][1] = 0.f;
-  }
-  for (int k0 = 0; k0 < T; k0 += TK) {
-    __syncthreads();
-    for (int i = t; i < TK * (kHeadDim / 4); i += DA_THREADS) {
-      const int r = i / (kHeadDim / 4), c = (i % (kHeadDim / 4)) * 4;
+  const __half *base = QKV16 + size_t(seq) * Tstride * 3072 + head * 192;
+
+  auto load_kv = [&](int kt, int buf) {
+    const int k0 = kt * TA_BK;
+    for (int i = tid; i < TA_BK * 16; i += NT) {
+      const int r = (i >> 3) & (TA_BK - 1), c = (i & 7) * 8, isv = i >> 9;
       const int kj = k0 + r;
-      float4 kv = make_float4(0, 0, 0, 0), vv = kv;
-      if (kj < T) {
-        kv = *reinterpret_cast<const float4 *>(base + size_t(kj) * 3072 + 64 + c);
-        vv = *reinterpret_cast<const float4 *>(base + size_t(kj) * 3072 + 128 + c);
-      }
-      *reinterpret_cast<float4 *>(&Ks[r][c]) = kv;
-      *reinterpret_cast<float4 *>(&Vs[r][c]) = vv;
+      const bool ok = kj < T;
+      const __half *src = base + size_t(ok ? kj : 0) * 3072 + (isv ? 128 : 64) + c;
+      ta_cp16(isv ? &Vs[buf][r][c] : &Ks[buf][r][c], src, ok);
+    }
+  };
+  for (int i = tid; i < BQ * 8; i += NT) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    const bool ok = q0 + r < T;
+    ta_cp16(&Qs[r][c], base + size_t(ok ? q0 + r : 0) * 3072 + c, ok);
+  }
+  load_kv(0, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (tid < 32) bias_s[tid] = 8.0f * kLog2e * relbias[tid * 16 + head];
+  __syncthreads();
+  // bt[j - qi + q0 + BQ - 1] for the block's queries qi in [q0, q0 + BQ) and every key j in [0, T)
+  for (int i = tid; i < T + BQ - 1; i += NT) {
+    const int d = i - (q0 + BQ - 1);
+    bt[i] = bias_s[(d > 0 ? 16 : 0) + rpb[min(abs(d), T - 1)]];
+  }
+
+  uint32_t qf[4][4];
+  float o[8][4], m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  const int nkt = (T + TA_BK - 1) / TA_BK;
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol = (lane >> 4) * 8;  // ldmatrix.x4 address pattern (A / V^T)
+  const int boff = BQ - 1 - warp * 16 - g;  // bias index of (row g, key j) = j + boff; row g + 8: - 8
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nkt) {
+      load_kv(kt + 1, buf ^ 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    float s[4][2];
+    if (kt == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s[i][0] = s[i][1] = 0.f;
-#pragma unroll 4
-    for (int c = 0; c < kHeadDim; c += 4) {
-      const float4 ka = *reinterpret_cast<const float4 *>(&Ks[lane][c]);
-      const float4 kb = *reinterpret_cast<const float4 *>(&Ks[lane + 32][c]);
+      for (int kk = 0; kk < 4; ++kk) ta_ldm4(qf[kk], &Qs[warp * 16 + lrow][kk * 16 + lcol]);
+    }
+    float s[8][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 qv = *reinterpret_cast<const float4 *>(&Qs[warp * 4 + i][c]);
-        s[i][0] += qv.x * ka.x + qv.y * ka.y + qv.z * ka.z + qv.w * ka.w;
-        s[i][1] += qv.x * kb.x + qv.y * kb.y + qv.z * kb.z + qv.w * kb.w;
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      uint32_t kf[4];
+      // K rows nt*8 .. +7: matrices = d chunks (lane / 8) * 8 of this half of the head dim
+      ta_ldm4(kf, &Ks[buf][nt * 8 + (lane & 7)][(lane >> 3) * 8]);
+      ta_mma(s[nt], qf[0], kf[0], kf[1]);
+      ta_mma(s[nt], qf[1], kf[2], kf[3]);
+      ta_ldm4(kf, &Ks[buf][nt * 8 + (lane & 7)][32 + (lane >> 3) * 8]);
+      ta_mma(s[nt], qf[2], kf[0], kf[1]);
+      ta_mma(s[nt], qf[3], kf[2], kf[3]);
+    }
+    const int k0 = kt * TA_BK;
+    float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = k0 + nt * 8 + 2 * t4 + e;
+        const bool ok = j < T;
+        const float a = ok ? fmaf(s[nt][e], 0.125f * kLog2e, bt[j + boff]) : -INFINITY;
+        const float b = ok ? fmaf(s[nt][2 + e], 0.125f * kLog2e, bt[j + boff - 8]) : -INFINITY;
+        s[nt][e] = a;
+        s[nt][2 + e] = b;
+        mx_lo = fmaxf(mx_lo, a);
+        mx_hi = fmaxf(mx_hi, b);
       }
     }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);  // finite: key k0 is always valid
+    const float c_lo = exp2f(m_lo - mn_lo), c_hi = exp2f(m_hi - mn_hi);
+    m_lo = mn_lo;
+    m_hi = mn_hi;
+    float ps_lo = 0.f, ps_hi = 0.f;
+    uint32_t pf[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int qi = q0 + warp * 4 + i;
-      const int j0 = k0 + lane, j1 = k0 + lane + 32;
-      float s0 = -INFINITY, s1 = -INFINITY;
-      if (qi < T && j0 < T) s0 = s[i][0] * 0.125f + bias_s[(j0 > qi ? 16 : 0) + rpb[abs(j0 - qi)]];
-      if (qi < T && j1 < T) s1 = s[i][1] * 0.125f + bias_s[(j1 > qi ? 16 : 0) + rpb[abs(j1 - qi)]];
-      const float tmax = warp_max(fmaxf(s0, s1));
-      const float mnew = fmaxf(m[i], tmax);
-      float p0 = 0.f, p1 = 0.f, corr = 1.f;
-      if (mnew != -INFINITY) {
-        p0 = expf(s0 - mnew);
-        p1 = expf(s1 - mnew);
-        corr = expf(m[i] - mnew);
-      }
-      l[i] = l[i] * corr + warp_sum(p0 + p1);
-      o[i][0] *= corr;
-      o[i][1] *= corr;
-      m[i] = mnew;
-      Ps[warp][i][lane] = p0;
-      Ps[warp][i][lane + 32] = p1;
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f(s[nt][0] - mn_lo), p1 = exp2f(s[nt][1] - mn_lo);
+      const float p2 = exp2f(s[nt][2] - mn_hi), p3 = exp2f(s[nt][3] - mn_hi);
+      ps_lo += p0 + p1;
+      ps_hi += p2 + p3;
+      pf[nt >> 1][(nt & 1) * 2] = ta_pack(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = ta_pack(p2, p3);
+      o[nt][0] *= c_lo;
+      o[nt][1] *= c_lo;
+      o[nt][2] *= c_hi;
+      o[nt][3] *= c_hi;
     }
-    __syncwarp();
-    const int kmax = min(TK, T - k0);
-    for (int j = 0; j < kmax; ++j) {
-      const float v0 = Vs[j][lane], v1 = Vs[j][lane + 32];
+    l_lo = l_lo * c_lo + ps_lo;
+    l_hi = l_hi * c_hi + ps_hi;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float p = Ps[warp][i][j];
-        o[i][0] = fmaf(p, v0, o[i][0]);
-        o[i][1] = fmaf(p, v1, o[i][1]);
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int dn = 0; dn < 8; dn += 2) {
+        uint32_t vf[4];
+        ta_ldm4_t(vf, &Vs[buf][kk * 16 + lrow][dn * 8 + lcol]);
+        ta_mma(o[dn], pf[kk], vf[0], vf[1]);
+        ta_mma(o[dn + 1], pf[kk], vf[2], vf[3]);
       }
     }
-    __syncwarp();
+    __syncthreads();  // every warp is done with this buffer before the tile after next lands in it
   }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int qi = q0 + warp * 4 + i;
-    if (qi < T) {
-      const float inv = 1.0f / l[i];
-      const size_t off = (size_t(seq) * Tstride + qi) * kDim + head * kHeadDim;
-      const float v0 = o[i][0] * inv, v1 = o[i][1] * inv;
-      const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-      out_hi[off + lane] = h0;
-      out_hi[off + lane + 32] = h1;
-      out_lo[off + lane] = __float2half_rn(v0 - __half2float(h0));
-      out_lo[off + lane + 32] = __float2half_rn(v1 - __half2float(h1));
+  for (int h = 0; h < 2; ++h) {
+    const int qi = q0 + warp * 16 + g + 8 * h;
+    if (qi >= T) continue;
+    const float inv = 1.0f / (h ? l_hi : l_lo);
+    const size_t off = (size_t(seq) * Tstride + qi) * kDim + head * kHeadDim + 2 * t4;
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) {
+      const float v0 = o[dn][2 * h] * inv, v1 = o[dn][2 * h + 1] * inv;
+      const __half2 hi = __floats2half2_rn(v0, v1);
+      const float2 back = __half22float2(hi);
+      *reinterpret_cast<__half2 *>(out_hi + off + dn * 8) = hi;
+      *reinterpret_cast<__half2 *>(out_lo + off + dn * 8) = __floats2half2_rn(v0 - back.x, v1 - back.y);
     }
   }
 }

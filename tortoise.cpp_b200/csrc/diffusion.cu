@@ -38,9 +38,9 @@ struct DiffModel {
   float *b_inp, *b_integ, *b_out, *out_gn_w, *out_gn_b;
   // work buffers
   int capS = 0, capSteps = 0, capU = 0;  // capacities: frames per sequence, sampling steps, utterances per batch
-  float *X = nullptr, *CW = nullptr, *CE = nullptr, *H1 = nullptr, *QKV = nullptr, *OUT = nullptr, *INP = nullptr;
+  float *X = nullptr, *CW = nullptr, *CE = nullptr, *H1 = nullptr, *OUT = nullptr, *INP = nullptr;
   float *stats = nullptr, *x_dev = nullptr, *noise_dev = nullptr, *lat_dev = nullptr;
-  __half *A16 = nullptr, *CAT16 = nullptr, *XIN16 = nullptr, *ATThi = nullptr, *ATTlo = nullptr;
+  __half *A16 = nullptr, *CAT16 = nullptr, *XIN16 = nullptr, *ATThi = nullptr, *ATTlo = nullptr, *QKV16 = nullptr;
   int *rpb = nullptr, *up_idx = nullptr;
   float *TE = nullptr, *T0 = nullptr, *TEMB = nullptr, *EMB = nullptr;
   __half *P_hi = nullptr, *P_lo = nullptr;  // [steps][1024] planes scratch
@@ -210,7 +210,7 @@ static void ensure_buffers(tts_ctx *c, int S, int steps, int U = 1) {
     grow(c, &m.CW, s2 * kDim);
     grow(c, &m.CE, s2 * kDim);
     grow(c, &m.H1, s2 * kDim);
-    grow(c, &m.QKV, s2 * 3072);
+    grow(c, &m.QKV16, s2 * 3072);
     grow(c, &m.OUT, s2 * 200);
     grow(c, &m.INP, size_t(U) * S * kDim);
     grow(c, &m.stats, nseq * 32 * 2);
@@ -249,10 +249,10 @@ static void ensure_buffers(tts_ctx *c, int S, int steps, int U = 1) {
 
 static void tg(tts_ctx *c, const Launcher &L, const __half *Ahi, const __half *Alo, const __half *Whi, const __half *Wlo,
                const float *bias, float *C, int M, int N, int K, int lda, int ldc, int epi, int taps = 1, int T = 0,
-               int halo = 0) {
+               int halo = 0, __half *C16 = nullptr) {
   DiffModel &m = *c->diff;
   const int Tt = T > 0 ? T : M;
-  TGemmArgs g{Ahi, Alo, Whi, Wlo, bias, C, nullptr, nullptr, M, N, K, lda, ldc, 0, epi, taps, 1, taps / 2, halo, Tt};
+  TGemmArgs g{Ahi, Alo, Whi, Wlo, bias, C, C16, nullptr, M, N, K, lda, ldc, C16 ? ldc : 0, epi, taps, 1, taps / 2, halo, Tt};
   g.Tseq = T > 0 ? m.tseq : nullptr;
   // outputs that feed a GroupNorm (x, h1, code embedding): let the epilogue produce the statistics
   const bool gn_target = T > 0 && N == kDim && (C == m.X || C == m.CW || C == m.H1) && Tt <= 64 * T5_BM;
@@ -292,10 +292,18 @@ static void res_block(tts_ctx *c, const Launcher &L, const DRes &r, float *x, in
 static void attn_block(tts_ctx *c, const Launcher &L, const DAttn &a, float *x, int nseq, int T) {
   DiffModel &m = *c->diff;
   gn(c, L, x, a.n_w, a.n_b, nullptr, m.A16, nullptr, nseq, T, 0);
-  conv(c, L, m.A16, a.w_qkv, a.b_qkv, m.QKV, nseq, T, kDim, 3072, 1, 3072, E_BIAS);
-  ensure_smem_attr(diff_attn_kernel, DA_SMEM);
-  L(diff_attn_kernel, dim3((T + DA_Q - 1) / DA_Q, kHeads, nseq), dim3(DA_THREADS), DA_SMEM, (const float *)m.QKV,
-    (const float *)a.relbias, (const int *)m.rpb, m.ATThi, m.ATTlo, T, m.tseq);
+  // q | k | v leave the GEMM's epilogue as f16 (the attention's tensor-core operands); no f32 copy is kept
+  tg(c, L, m.A16, nullptr, a.w_qkv, nullptr, a.b_qkv, nullptr, nseq * T, 3072, kDim, kDim, 3072, E_BIAS, 1, T, 1, m.QKV16);
+  // 64 queries per block once that fills the SMs twice over, else 32 (S = 191: 192 blocks instead of 96)
+  if (((T + 63) / 64) * kHeads * nseq >= 2 * 148) {
+    ensure_smem_attr(diff_attn_tc_kernel<4>, ta_smem_bytes<4>(4096));
+    L(diff_attn_tc_kernel<4>, dim3((T + 63) / 64, kHeads, nseq), dim3(128), ta_smem_bytes<4>(T), (const __half *)m.QKV16,
+      (const float *)a.relbias, (const int *)m.rpb, m.ATThi, m.ATTlo, T, m.tseq);
+  } else {
+    ensure_smem_attr(diff_attn_tc_kernel<2>, ta_smem_bytes<2>(4096));
+    L(diff_attn_tc_kernel<2>, dim3((T + 31) / 32, kHeads, nseq), dim3(64), ta_smem_bytes<2>(T), (const __half *)m.QKV16,
+      (const float *)a.relbias, (const int *)m.rpb, m.ATThi, m.ATTlo, T, m.tseq);
+  }
   tg(c, L, m.ATThi, m.ATTlo, a.proj_hi, a.proj_lo, a.b_proj, x, nseq * T, kDim, kDim, kDim, kDim, E_BIAS_RESID,
      1, T, 0);  // per-sequence M tiles so the fused GroupNorm statistics stay per sequence
 }
@@ -444,7 +452,7 @@ static int count_kernel_nodes(cudaGraph_t graph) {
 void diff_debug_read(tts_ctx *c, int which, float *out, size_t n) {
   if (!c->diff) throw ArgError("diffusion model not loaded");
   DiffModel &m = *c->diff;
-  const float *src = which == 0 ? m.CW : which == 1 ? m.X : which == 2 ? m.OUT : which == 3 ? m.INP : which == 4 ? m.QKV : which == 6 ? m.CE : which == 7 ? reinterpret_cast<const float *>(m.ATThi) : m.H1;
+  const float *src = which == 0 ? m.CW : which == 1 ? m.X : which == 2 ? m.OUT : which == 3 ? m.INP : which == 6 ? m.CE : which == 7 ? reinterpret_cast<const float *>(m.ATThi) : m.H1;
   TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   TTS_CUDA_TRY(cudaMemcpy(out, src, n * 4, cudaMemcpyDeviceToHost));
 }
