@@ -65,6 +65,74 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank
   return v;
 }
 
+// rows [row_base, row_base + rows_per) of the tile: split-K sum over the cluster's partial tiles, epilogue, stores.
+// EPI is a template parameter: with the epilogue kind read from the kernel argument every element went through an
+// indirect branch (LDC + BRX, four per row and lane) and the loop ran at ~450 ns per row -- 7.4 us of a 26 us GEMM
+// at csz = 1, 4.3 us of 11.7 at csz = 4 (tc5trace, round 2).
+template <int EPI>
+__device__ __forceinline__ void t6_epilogue_rows(const TGemmArgs &g, const float *red, int csz, int rows_per, int row_base,
+                                                 int rows_valid, int m0, int n, int c, bool vec, const float (&bias)[4], int warp,
+                                                 bool do_gn, double &gs1, double &gs2) {
+  constexpr bool resid = EPI == E_BIAS_RESID || EPI == E_BIAS_LRELU_RESID;
+  const uint32_t red_u32 = smem_u32(red);
+  for (int rr = warp; rr < rows_per; rr += 8) {
+    const int r = row_base + rr;
+    if (r >= rows_valid) break;
+    const uint32_t off = uint32_t(r * T6_RED_LD + c) * 4;
+    float4 a4;
+    if (csz == 1) {
+      a4 = *reinterpret_cast<const float4 *>(red + size_t(r) * T6_RED_LD + c);
+    } else {
+      float4 p[8];  // every rank's partial in flight before the first use; summed in rank order (deterministic)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < csz) p[k] = ld_dsmem_f4(red_u32 + off, k);
+      a4 = p[0];
+#pragma unroll
+      for (int k = 1; k < 8; ++k)
+        if (k < csz) { a4.x += p[k].x; a4.y += p[k].y; a4.z += p[k].z; a4.w += p[k].w; }
+    }
+    const int m = m0 + r;
+    float acc[4] = {a4.x, a4.y, a4.z, a4.w}, out[4];
+    if (vec) {
+      float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (resid) o4 = *reinterpret_cast<const float4 *>(g.C + size_t(m) * g.ldc + n);
+      const float old[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) out[e] = apply_epi(EPI, acc[e], bias[e], old[e]);
+      if (g.C) *reinterpret_cast<float4 *>(g.C + size_t(m) * g.ldc + n) = make_float4(out[0], out[1], out[2], out[3]);
+      if (g.Chi) {
+        __half hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          hi[e] = __float2half_rn(out[e]);
+          lo[e] = __float2half_rn(out[e] - __half2float(hi[e]));
+        }
+        *reinterpret_cast<uint2 *>(g.Chi + size_t(m) * g.ldh + n) = *reinterpret_cast<uint2 *>(hi);
+        if (g.Clo) *reinterpret_cast<uint2 *>(g.Clo + size_t(m) * g.ldh + n) = *reinterpret_cast<uint2 *>(lo);
+      }
+      if (do_gn) {
+        // 4-value partials in f32 (relative error 1e-7, the rounding of the values themselves), rows summed in double:
+        // two conversions and two additions per row on the FP64 pipe instead of fifteen
+        gs1 += double((out[0] + out[1]) + (out[2] + out[3]));
+        gs2 += double((out[0] * out[0] + out[1] * out[1]) + (out[2] * out[2] + out[3] * out[3]));
+      }
+    } else {
+      for (int e = 0; e < 4 && n + e < g.N; ++e) {
+        float old = 0.f;
+        if (resid) old = g.C[size_t(m) * g.ldc + n + e];
+        const float o = apply_epi(EPI, acc[e], bias[e], old);
+        if (g.C) g.C[size_t(m) * g.ldc + n + e] = o;
+        if (g.Chi) {
+          const __half hi = __float2half_rn(o);
+          g.Chi[size_t(m) * g.ldh + n + e] = hi;
+          if (g.Clo) g.Clo[size_t(m) * g.ldh + n + e] = __float2half_rn(o - __half2float(hi));
+        }
+      }
+    }
+  }
+}
+
 static __global__ void __launch_bounds__(T6_THREADS, T6_MIN_CTAS)
     tc5v2_kernel(TGemmArgs g, const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                  const __grid_constant__ CUtensorMap mWhi, const __grid_constant__ CUtensorMap mWlo, int csz,
@@ -235,61 +303,14 @@ static __global__ void __launch_bounds__(T6_THREADS, T6_MIN_CTAS)
       for (int e = 0; e < 4; ++e)
         if (n + e < g.N) bias[e] = g.bias[n + e];
     }
-    const bool resid = g.epi == E_BIAS_RESID || g.epi == E_BIAS_LRELU_RESID;
-    const uint32_t red_u32 = smem_u32(red);
     double gs1 = 0.0, gs2 = 0.0;
-    // (A variant with two rows per warp and all 2 x csz distributed-shared-memory reads of a pass in
-    // flight before the first use measured no faster -- 118.6 vs 112.6 ms for the 80-step stage: the
-    // reduction is bound by DSMEM bandwidth (17-21 B/cycle/SM for the 64 KB a CTA has to read), not
-    // by the latency of dependent loads.)
-    for (int rr = warp; rr < rows_per; rr += 8) {
-      const int r = row_base + rr;
-      if (r >= rows_valid) break;
-      const uint32_t off = uint32_t(r * T6_RED_LD + c) * 4;
-      float4 a4;
-      if (csz == 1) {
-        a4 = *reinterpret_cast<const float4 *>(red + size_t(r) * T6_RED_LD + c);
-      } else {
-        a4 = ld_dsmem_f4(red_u32 + off, 0);
-        for (int k = 1; k < csz; ++k) {
-          const float4 p = ld_dsmem_f4(red_u32 + off, k);
-          a4.x += p.x; a4.y += p.y; a4.z += p.z; a4.w += p.w;
-        }
-      }
-      const int m = m0 + r;
-      float acc[4] = {a4.x, a4.y, a4.z, a4.w}, out[4];
-      if (vec) {
-        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (resid) o4 = *reinterpret_cast<const float4 *>(g.C + size_t(m) * g.ldc + n);
-        const float old[4] = {o4.x, o4.y, o4.z, o4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) out[e] = apply_epi(g.epi, acc[e], bias[e], old[e]);
-        if (g.C) *reinterpret_cast<float4 *>(g.C + size_t(m) * g.ldc + n) = make_float4(out[0], out[1], out[2], out[3]);
-        if (g.Chi) {
-          __half hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            hi[e] = __float2half_rn(out[e]);
-            lo[e] = __float2half_rn(out[e] - __half2float(hi[e]));
-          }
-          *reinterpret_cast<uint2 *>(g.Chi + size_t(m) * g.ldh + n) = *reinterpret_cast<uint2 *>(hi);
-          if (g.Clo) *reinterpret_cast<uint2 *>(g.Clo + size_t(m) * g.ldh + n) = *reinterpret_cast<uint2 *>(lo);
-        }
-        gs1 += (double(out[0]) + double(out[1])) + (double(out[2]) + double(out[3]));
-        gs2 += (double(out[0]) * out[0] + double(out[1]) * out[1]) + (double(out[2]) * out[2] + double(out[3]) * out[3]);
-      } else {
-        for (int e = 0; e < 4 && n + e < g.N; ++e) {
-          float old = 0.f;
-          if (resid) old = g.C[size_t(m) * g.ldc + n + e];
-          const float o = apply_epi(g.epi, acc[e], bias[e], old);
-          if (g.C) g.C[size_t(m) * g.ldc + n + e] = o;
-          if (g.Chi) {
-            const __half hi = __float2half_rn(o);
-            g.Chi[size_t(m) * g.ldh + n + e] = hi;
-            if (g.Clo) g.Clo[size_t(m) * g.ldh + n + e] = __float2half_rn(o - __half2float(hi));
-          }
-        }
-      }
+    const bool do_gn = g.gn_partial != nullptr;
+    switch (g.epi) {
+#define T6_CASE(E) case E: t6_epilogue_rows<E>(g, red, csz, rows_per, row_base, rows_valid, m0, n, c, vec, bias, warp, do_gn, gs1, gs2); break;
+      T6_CASE(E_NONE) T6_CASE(E_BIAS) T6_CASE(E_BIAS_H16) T6_CASE(E_BIAS_GELU16) T6_CASE(E_BIAS_RESID) T6_CASE(E_BIAS_LRELU)
+      T6_CASE(E_BIAS_LRELU_RESID)
+#undef T6_CASE
+      default: break;
     }
     if (tid == 0) trace(10);
     if (g.gn_partial) {
