@@ -57,6 +57,10 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x));
 // (main.cpp:3356-3372 norm+affine, 3449-3452 scale/shift, 3373/3454 silu; the conv's im2col
 // rounds to f16, ggml.c:6493-6508.)  ss_stride: elements between the sequences' ss vectors.
 // grid (T + 2*halo, nseq) x 256.
+// grid (ceil((T + 2*halo) / R), nseq) x 256: a block normalises R rows -- the statistics, affine and scale/shift
+// vectors are fetched once and the R row loads are in flight together (one row per block was three dependent
+// L2 round trips for 4 KB: 13.7 us per call at S = 1306, 1.2 TB/s).
+template <int R>
 static __global__ void __launch_bounds__(256) gn_apply_kernel(const float *X, const float *stats, const float *w,
                                                        const float *b, const float *ss, __half *out16,
                                                        float *out32, int T, int halo, int ldo, int silu,
@@ -67,59 +71,72 @@ static __global__ void __launch_bounds__(256) gn_apply_kernel(const float *X, co
   // the per-timestep scale|shift table advances with a device-side step counter so that one
   // captured CUDA graph serves every sampling step
   if (ss && step_ptr) ss += size_t(*step_ptr) * ss_step_stride;
-  const int row = blockIdx.x, seq = blockIdx.y, tid = threadIdx.x;
-  const int t = row - halo;
+  const int row0 = blockIdx.x * R, seq = blockIdx.y, tid = threadIdx.x;
   const int c = tid * 4;
   const int Ts = Tseq ? Tseq[seq] : T;  // valid frames of this sequence (T is the common row stride)
-  float v[4] = {0.f, 0.f, 0.f, 0.f};
-  if (t >= 0 && t < Ts) {
-    const float4 x = *reinterpret_cast<const float4 *>(X + (size_t(seq) * T + t) * kDim + c);
-    const int g = c >> 5;
-    float mean, rstd;
-    if (partial) {
-      // statistics fused into the producing GEMM's epilogue: {sum, sumsq} per M tile, in double
-      double s1 = 0.0, s2 = 0.0;
-      for (int i = 0; i < mtiles; ++i) {
-        s1 += partial[((size_t(seq) * 32 + g) * mtiles + i) * 2];
-        s2 += partial[((size_t(seq) * 32 + g) * mtiles + i) * 2 + 1];
+  const int nrows = T + 2 * halo;
+  float4 x[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int t = row0 + i - halo;
+    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < Ts) x[i] = *reinterpret_cast<const float4 *>(X + (size_t(seq) * T + t) * kDim + c);
+  }
+  const int g = c >> 5;
+  float mean, rstd;
+  if (partial) {
+    // statistics fused into the producing GEMM's epilogue but not reduced there: {sum, sumsq} per M tile, in double
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < mtiles; ++i) {
+      s1 += partial[((size_t(seq) * 32 + g) * mtiles + i) * 2];
+      s2 += partial[((size_t(seq) * 32 + g) * mtiles + i) * 2 + 1];
+    }
+    const double n = double(Ts) * 32.0, md = s1 / n;
+    mean = float(md);
+    double var = s2 / n - 2.0 * md * double(mean) + double(mean) * double(mean);  // E[(x - mean_f)^2]
+    if (var < 0.0) var = 0.0;
+    rstd = 1.0f / sqrtf(float(var) + 1e-6f);
+  } else {
+    mean = stats[(seq * 32 + g) * 2];
+    rstd = stats[(seq * 32 + g) * 2 + 1];
+  }
+  const float4 w4 = *reinterpret_cast<const float4 *>(w + c);
+  const float4 b4 = *reinterpret_cast<const float4 *>(b + c);
+  float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+  if (ss) {
+    sc = *reinterpret_cast<const float4 *>(ss + c);
+    sh = *reinterpret_cast<const float4 *>(ss + kDim + c);
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int row = row0 + i, t = row - halo;
+    if (row >= nrows) break;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool live = t >= 0 && t < Ts;
+    if (live) {
+      v[0] = (x[i].x - mean) * rstd * w4.x + b4.x;
+      v[1] = (x[i].y - mean) * rstd * w4.y + b4.y;
+      v[2] = (x[i].z - mean) * rstd * w4.z + b4.z;
+      v[3] = (x[i].w - mean) * rstd * w4.w + b4.w;
+      if (ss) {
+        v[0] = v[0] * (sc.x + 1.0f) + sh.x;
+        v[1] = v[1] * (sc.y + 1.0f) + sh.y;
+        v[2] = v[2] * (sc.z + 1.0f) + sh.z;
+        v[3] = v[3] * (sc.w + 1.0f) + sh.w;
       }
-      const double n = double(Ts) * 32.0, md = s1 / n;
-      mean = float(md);
-      double var = s2 / n - 2.0 * md * double(mean) + double(mean) * double(mean);  // E[(x - mean_f)^2]
-      if (var < 0.0) var = 0.0;
-      rstd = 1.0f / sqrtf(float(var) + 1e-6f);
-    } else {
-      mean = stats[(seq * 32 + g) * 2];
-      rstd = stats[(seq * 32 + g) * 2 + 1];
-    }
-    const float4 w4 = *reinterpret_cast<const float4 *>(w + c);
-    const float4 b4 = *reinterpret_cast<const float4 *>(b + c);
-    v[0] = (x.x - mean) * rstd * w4.x + b4.x;
-    v[1] = (x.y - mean) * rstd * w4.y + b4.y;
-    v[2] = (x.z - mean) * rstd * w4.z + b4.z;
-    v[3] = (x.w - mean) * rstd * w4.w + b4.w;
-    if (ss) {
-      const float4 sc = *reinterpret_cast<const float4 *>(ss + c);
-      const float4 sh = *reinterpret_cast<const float4 *>(ss + kDim + c);
-      v[0] = v[0] * (sc.x + 1.0f) + sh.x;
-      v[1] = v[1] * (sc.y + 1.0f) + sh.y;
-      v[2] = v[2] * (sc.z + 1.0f) + sh.z;
-      v[3] = v[3] * (sc.w + 1.0f) + sh.w;
-    }
-    if (silu) {
+      if (silu) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = silu_f(v[i]);
+        for (int e = 0; e < 4; ++e) v[e] = silu_f(v[e]);
+      }
     }
-  }
-  if (out16) {
-    __half h[4];
+    if (out16) {
+      __half h[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __float2half_rn(v[i]);
-    *reinterpret_cast<uint2 *>(out16 + (size_t(seq) * (T + 2 * halo) + row) * ldo + c) =
-        *reinterpret_cast<uint2 *>(h);
+      for (int e = 0; e < 4; ++e) h[e] = __float2half_rn(v[e]);
+      *reinterpret_cast<uint2 *>(out16 + (size_t(seq) * nrows + row) * ldo + c) = *reinterpret_cast<uint2 *>(h);
+    }
+    if (out32 && live) *reinterpret_cast<float4 *>(out32 + (size_t(seq) * T + t) * kDim + c) = make_float4(v[0], v[1], v[2], v[3]);
   }
-  if (out32 && t >= 0 && t < Ts)
-    *reinterpret_cast<float4 *>(out32 + (size_t(seq) * T + t) * kDim + c) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // f32 [T][C] -> f16 [T + 2*halo][ldo] with zero halo rows and zero channel padding.
@@ -214,7 +231,7 @@ static __global__ void silu_split_kernel(const float *in, __half *hi, __half *lo
 constexpr int TA_BK = 64, TA_LD = kHeadDim + 8;  // 72 halves per row: ldmatrix rows fall on distinct banks
 template <int NW>
 constexpr size_t ta_smem_bytes(int T) {
-  return size_t(16 * NW + 4 * TA_BK) * TA_LD * sizeof(__half) + size_t(T + 16 * NW) * sizeof(float) + 32 * sizeof(float);
+  return size_t(4 * TA_BK) * TA_LD * sizeof(__half) + size_t(T + 16 * NW) * sizeof(float) + 32 * sizeof(float);
 }
 __device__ __forceinline__ void ta_cp16(void *dst, const void *src, bool valid) {
   const int n = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
@@ -242,15 +259,16 @@ __device__ __forceinline__ uint32_t ta_pack(float a, float b) {
 
 // grid (ceil(T / (16 NW)), 16 heads, nseq) x 32 NW
 template <int NW>
-static __global__ void __launch_bounds__(NW * 32) diff_attn_tc_kernel(const __half *QKV16, const float *relbias, const int *rpb,
+static __global__ void __launch_bounds__(NW * 32, NW == 4 ? 5 : 8) diff_attn_tc_kernel(const __half *QKV16, const float *relbias, const int *rpb,
                                                                __half *out_hi, __half *out_lo, int Tstride, const int *Tseq) {
   constexpr int BQ = 16 * NW, NT = NW * 32, LD = TA_LD;
   constexpr float kLog2e = 1.4426950408889634f;
   extern __shared__ __align__(16) unsigned char ta_raw[];
-  __half (*Qs)[LD] = reinterpret_cast<__half (*)[LD]>(ta_raw);
-  __half (*Ks)[TA_BK][LD] = reinterpret_cast<__half (*)[TA_BK][LD]>(ta_raw + size_t(BQ) * LD * 2);
-  __half (*Vs)[TA_BK][LD] = reinterpret_cast<__half (*)[TA_BK][LD]>(ta_raw + size_t(BQ + 2 * TA_BK) * LD * 2);
-  float *bias_s = reinterpret_cast<float *>(ta_raw + size_t(BQ + 4 * TA_BK) * LD * 2);
+  __half (*Ks)[TA_BK][LD] = reinterpret_cast<__half (*)[TA_BK][LD]>(ta_raw);
+  __half (*Vs)[TA_BK][LD] = reinterpret_cast<__half (*)[TA_BK][LD]>(ta_raw + size_t(2 * TA_BK) * LD * 2);
+  __half (*Qs)[LD] = Ks[1];  // the query tile passes through the second K buffer on its way to registers
+  float *bias_s = reinterpret_cast<float *>(ta_raw + size_t(4 * TA_BK) * LD * 2);
+  static_assert(BQ <= TA_BK, "the query tile is staged in one K buffer");
   float *bt = bias_s + 32;
   pdl_launch_dependents();
   pdl_wait();
@@ -286,6 +304,11 @@ static __global__ void __launch_bounds__(NW * 32) diff_attn_tc_kernel(const __ha
   }
 
   uint32_t qf[4][4];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) ta_ldm4(qf[kk], &Qs[warp * 16 + ((lane & 7) + ((lane >> 3) & 1) * 8)][kk * 16 + (lane >> 4) * 8]);
+  __syncthreads();  // every warp holds its query fragments: the buffer is free for key tile 1
   float o[8][4], m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
@@ -302,10 +325,6 @@ static __global__ void __launch_bounds__(NW * 32) diff_attn_tc_kernel(const __ha
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    if (kt == 0) {
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) ta_ldm4(qf[kk], &Qs[warp * 16 + lrow][kk * 16 + lcol]);
-    }
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {

@@ -274,8 +274,14 @@ static void gn(tts_ctx *c, const Launcher &L, const float *X, const float *w, co
   const bool fused = m.partial_src == X;
   if (out32 && out32 == m.partial_src) m.partial_src = nullptr;  // about to be overwritten
   if (!fused) L(gn_stats_kernel, dim3(32, nseq), dim3(256), 0, X, m.stats, T, m.tseq);
-  L(gn_apply_kernel, dim3(T + 2, nseq), dim3(256), 0, X, (const float *)m.stats, w, b, ss, out16, out32, T, 1, kDim,
-    silu, (const int *)m.d_step, 16 * 2048, (const double *)(fused ? m.gn_partial : nullptr), m.partial_mtiles, m.tseq);
+  const double *partial = fused ? m.gn_partial : nullptr;
+  // 8 rows per block once that still fills the SMs twice, else 2 (S = 191: 194 blocks)
+  if ((T + 2 + 7) / 8 * nseq >= 2 * 148)
+    L(gn_apply_kernel<8>, dim3((T + 2 + 7) / 8, nseq), dim3(256), 0, X, (const float *)m.stats, w, b, ss, out16, out32, T, 1, kDim,
+      silu, (const int *)m.d_step, 16 * 2048, partial, m.partial_mtiles, m.tseq);
+  else
+    L(gn_apply_kernel<2>, dim3((T + 2 + 1) / 2, nseq), dim3(256), 0, X, (const float *)m.stats, w, b, ss, out16, out32, T, 1, kDim,
+      silu, (const int *)m.d_step, 16 * 2048, partial, m.partial_mtiles, m.tseq);
 }
 
 // ResBlock (main.cpp:3347-3480): x += conv3(silu((GN(h)w+b)(1+scale)+shift)),
