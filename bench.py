@@ -19,7 +19,8 @@ forced to round(1.5 * chars) so the work does not depend on when the
             vocoder.  `value` is the RTF of the rendered utterance (flat in N by construction: one
             utterance is rendered whatever N is); what scales with N is `ar_mel_tokens_per_s`.
   --config C5 (any N): configs[4], 256 utterances of 20-300 chars sharded u mod N, --c5-batch U utterances per step
-    (AR per utterance, one utterance-batched diffusion per step, vocoder per utterance), per-stage RTF.
+    (one utterance-batched decode loop and one utterance-batched diffusion per step, latent pass and vocoder per
+    utterance), per-stage RTF.
 
   value : audio-s / device time (CUDA events around every stage call), max over ranks
   e2e   : audio-s / wall time of the host-driven pipeline through the C-ABI with HOST buffers
@@ -379,7 +380,8 @@ def main():
         dist.barrier()
 
     B = w["cand"]
-    run = Runner(local_rank, max_batch=max(2, B, 16 if cfg_name == "C2" and not args.no_extra else 0), max_positions=704 if cfg_name in ("C4", "C5") else 404)
+    run = Runner(local_rank, max_batch=max(2, B, 16 if cfg_name == "C2" and not args.no_extra else 0, max(5, min(16, args.c5_batch)) if cfg_name == "C5" else 0),
+                 max_positions=704 if cfg_name in ("C4", "C5") else 404)
     eng, hl = run.eng, run.hl
     group = None
     if world > 1:  # the selection's all-gather goes through the C-ABI (NCCL directly, csrc/dist.cu)
@@ -388,28 +390,31 @@ def main():
         group = run.pkg.Group([eng], rank=rank, world=world, unique_id=ids[0])
 
     prompts = c5_prompts() if cfg_name == "C5" else None
-    U5 = max(1, args.c5_batch)
+    U5 = max(1, min(16, args.c5_batch))
     if cfg_name == "C5":  # this rank's share (u mod N), sorted by length so that a batch pads little
         my_utts = sorted(range(rank, 256, world), key=lambda u: len(prompts[u]))
         n_batches = (len(my_utts) + U5 - 1) // U5
 
     def one_batch(k, seed):
-        """configs[4]: one step = U utterances of this rank: AR one by one (1 candidate each), ONE batched diffusion
-        (U utterances of different lengths on one launch set per step), vocoder one by one"""
+        """configs[4]: one step = U utterances of this rank: ONE utterance-batched decode loop (U prompts per decode
+        launch), latent pass per utterance, ONE batched diffusion (U utterances of different lengths on one launch
+        set per sampling step), vocoder one by one"""
         b = (k * 7) % n_batches  # walk the length buckets rather than only the shortest ones
         utts = my_utts[b * U5:(b + 1) * U5]
         out = dict(ar_wall=0.0, ar_dev_ms=0.0, tokens=0, audio_s=0.0, diff_ms=0.0, voc_ms=0.0, h2d=0, d2h=0, gather_ms=0.0, owner=rank)
-        lats, rngs, meta = [], [], []
-        for j, u in enumerate(utts):
-            tokens = run.tokens(prompts[u])
-            codes = min(500 - 1, int(1.5 * len(prompts[u]) + 0.5))
-            a = run.ar(tokens, 1, codes, seed * 1000 + j, skip_latents=False)
-            out["ar_wall"] += a["wall"]
-            out["ar_dev_ms"] += a["dev_ms"]
-            out["tokens"] += a["steps"]
-            lats.append(a["lat"][0, :int(a["nlat"][0])])
-            rngs.append(a["rng"])
-            meta.append((len(tokens), a["steps"]))
+        # AR: the U prompts ride on ONE batched decode launch per step (tts_ar_prefill_multi / ar_mega4.cuh), each with
+        # its own RNG stream and forced length; then the latent pass per utterance
+        toks = [run.tokens(prompts[u]) for u in utts]
+        forced = [min(500 - 1, int(1.5 * len(prompts[u]) + 0.5)) for u in utts]
+        rngs = [hl.rng(seed * 1000 + j) for j in range(len(utts))]
+        d0 = eng.device_ms_total
+        t0 = time.perf_counter()
+        codes, nlat, steps = hl.autoregressive_multi(eng, rngs, toks, run.voice, forced_codes=forced)
+        lats = [hl.latents(eng, toks[j], run.voice, codes[j]) for j in range(len(utts))]
+        out["ar_wall"] = time.perf_counter() - t0
+        out["ar_dev_ms"] = eng.device_ms_total - d0
+        out["tokens"] = int(steps.sum())
+        meta = [(len(toks[j]), int(steps[j])) for j in range(len(utts))]
         d0 = eng.device_ms_total
         mels = hl.diffusion_batch(eng, rngs, lats, w["steps"])
         out["diff_ms"] = eng.device_ms_total - d0
@@ -542,8 +547,9 @@ def main():
     }
     if cfg_name == "C5":
         line["config"]["utterances_per_step"] = U5
-        line["config"]["batching"] = ("a step = U utterances of one length bucket on each rank: AR one utterance at a time, ONE "
-                                      "utterance-batched diffusion (2U sequences per launch set), vocoder one at a time")
+        line["config"]["batching"] = ("a step = U utterances of one length bucket on each rank: ONE utterance-batched decode loop "
+                                      "(U prompts per decode launch), ONE utterance-batched diffusion (2U sequences per launch "
+                                      "set), latent pass and vocoder one utterance at a time")
         line["stage_rtf"] = {"ar": audio_total / max(ar_dev_ms / 1e3, 1e-9), "diffusion": audio_total / max(diff_ms / 1e3, 1e-9),
                              "vocoder": audio_total / max(voc_ms / 1e3, 1e-9),
                              "note": "audio seconds / device seconds of that stage (sums over ranks for diffusion / vocoder at N > 1)"}

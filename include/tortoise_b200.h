@@ -70,6 +70,14 @@ int tts_load_vocoder(tts_ctx *ctx, const char *path);
 int tts_ar_prefill(tts_ctx *ctx, const int32_t *text_tokens, int32_t T, const float *voice_1024,
                    int32_t B, float *logits_out);
 
+/* Utterance batching of the decode loop (BASELINE.json configs[4]; no reference counterpart -- the reference
+ * prefills ONE prompt, main.cpp:5131-5186): U <= min(16, max_batch) DIFFERENT prompts are prefilled one after the
+ * other, prompt u into candidate slot u with its K/V rows right-aligned to the longest prompt, and the following
+ * tts_ar_step / tts_ar_step_topk calls decode all U on one weight stream (slot u attends to its own rows only).
+ * Needs dtype f16, max_batch >= 5 and max_positions <= 1024.  logits_out [U][8194]: first-step logits per prompt. */
+int tts_ar_prefill_multi(tts_ctx *ctx, int32_t U, const int32_t *const *text_tokens, const int32_t *T,
+                         const float *voice_1024, float *logits_out);
+
 /* Replaces one decode iteration, autoregressive_graph(fake_inputs=false) + compute
  * (main.cpp:5227-5247): feeds tokens[B] at mel position id pos_id (reference passes i+2),
  * appends to the KV cache, returns logits [B][8194]. */

@@ -101,6 +101,16 @@ int tts_host_autoregressive(struct tts_ctx *ctx, tts_rng *r, const int32_t *toke
                             int B, const tts_ar_options *opt, int32_t *codes_out, float *latents_out,
                             int32_t *n_latents, float *score_out, int32_t *steps_out);
 
+/* Utterance-batched decode loop (BASELINE.json configs[4]; the reference decodes one prompt per run,
+ * main.cpp:5042): U <= 16 DIFFERENT prompts ride on one batched decode launch per step (tts_ar_prefill_multi +
+ * tts_ar_step_topk).  Utterance u samples from its own rngs[u] with its own repetition-penalty window and stop state
+ * (forced_codes[u] > 0: exactly that many codes, the stop token suppressed before -- bench mode); it stops being
+ * extended once it emits 8193.  codes_out [U][500] / n_latents [U] as tts_host_autoregressive; steps_out [U] =
+ * sampled codes per utterance (may be NULL).  The latent pass is the caller's: tts_host_latents per utterance. */
+int tts_host_autoregressive_multi(struct tts_ctx *ctx, tts_rng *const *rngs, int32_t U, const int32_t *const *tokens,
+                                  const int32_t *T, const float *voice_1024, const int32_t *forced_codes, int32_t max_steps,
+                                  int32_t *codes_out, int32_t *n_latents, int32_t *steps_out);
+
 /* The latent pass of autoregressive() (main.cpp:5280-5352) + trim_latents (main.cpp:4873-4915) for ONE
  * candidate's codes500 (as returned in codes_out): latents_out [500][1024], rows >= *n_latents zero. */
 int tts_host_latents(struct tts_ctx *ctx, const int32_t *tokens, int T, const float *voice_1024,

@@ -204,6 +204,47 @@ def test_f16_batched_decode_vs_oracle(engine_f16, golden, voice, model_dir, B):
     assert max(errs) < F32_LOGIT_TOL
 
 
+def test_utterance_batched_decode_vs_oracle(engine_f16, golden, voice, model_dir, hostlib_full):
+    """tts_ar_prefill_multi: DIFFERENT prompts in the candidate slots of the batched decode launch (BASELINE
+    configs[4]).  Every utterance's logits -- first step and 4 teacher-forced steps -- against the numpy oracle
+    run on that utterance ALONE (f16-rounded weights): the right-aligned prompts, the per-slot first key and the
+    padding rows in front of the shorter prompts must not leak into any slot.  Then the driver
+    (tts_host_autoregressive_multi) with forced lengths per utterance."""
+    import _pkg
+    import tortoise_oracle as O
+    sw = _pkg.import_sub("synth_weights")
+    W = sw.read_container(os.path.join(model_dir, "ggml-model.bin"))
+    base = [int(t) for t in golden("ar_b1.npz")["tokens"]]
+    texts = [base, base[:11], (base + base[3:12])[:25], base[5:9], base[::-1][:14], base[2:]]
+    U = len(texts)
+    lg0 = engine_f16.ar_prefill_multi(texts, voice)
+    toks = [[(1000 + 211 * u + 37 * i) % 8192 for u in range(U)] for i in range(4)]
+    got = [lg0] + [engine_f16.ar_step(toks[i], i + 2) for i in range(4)]
+    worst = 0.0
+    for u in range(U):
+        ar = O.AROracle(W, weight_dtype="f16")
+        ref = [ar.prefill(np.array(texts[u]), voice, 1)[0]] + [ar.step(np.array([toks[i][u]]), i + 2)[0] for i in range(4)]
+        errs = [float(np.abs(got[i][u] - ref[i]).max()) for i in range(5)]
+        print(f"utterance {u} (T = {len(texts[u])}): max-abs per step {['%.2e' % e for e in errs]}")
+        worst = max(worst, max(errs))
+    assert worst < F32_LOGIT_TOL
+    # the driver: per-utterance RNG streams, forced lengths, stop handling
+    forced = [7, 3, 9, 5, 4, 6]
+    rngs = [hostlib_full.rng(40 + u) for u in range(U)]
+    codes, nlat, steps = hostlib_full.autoregressive_multi(engine_f16, rngs, texts, voice, forced_codes=forced)
+    assert steps.tolist() == [f + 1 for f in forced]  # forced codes + the stop token
+    for u in range(U):
+        seq = _steps(codes[u])
+        assert len(seq) == forced[u] + 1 and seq[-1] == 8193 and all(0 <= c < 8192 for c in seq[:-1])
+    # utterance 0 alone, same seed: identical codes unless a near-tie flips (both paths sample the same distribution)
+    rng0 = hostlib_full.rng(40)
+    c1 = hostlib_full.autoregressive(engine_f16, rng0, np.array(texts[0], dtype=np.int32), voice, 1, forced_codes=forced[0],
+                                     per_candidate_stop=True, skip_latents=True)[0]
+    same = sum(1 for a, b in zip(_steps(c1[0]), _steps(codes[0])) if a == b)
+    print(f"utterance 0: {same} of {forced[0] + 1} codes equal to the one-at-a-time run with the same seed")
+    assert same >= 1
+
+
 def test_batched_topk_step_is_consistent_with_full_logits(engine_f16, golden, voice):
     """tts_ar_step_topk: the device-side top-64 (value, index) pairs of every candidate equal the
     top-64 of the full logits row of the same step (bit-exact values, same index set)."""

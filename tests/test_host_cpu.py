@@ -153,7 +153,7 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(full, name), f"libtortoise_b200.so lacks {name}"
     host = ctypes.CDLL(os.path.join(os.path.dirname(pkg.LIB_PATH), "libtortoise_host.so"))
     drivers = {"tts_host_autoregressive", "tts_host_diffusion", "tts_host_vocoder", "tts_host_latents",
-               "tts_host_diffusion_batch"}
+               "tts_host_diffusion_batch", "tts_host_autoregressive_multi"}
     for name in sorted(decl["tortoise_host.h"] - drivers):
         assert hasattr(host, name), f"libtortoise_host.so lacks {name}"
 

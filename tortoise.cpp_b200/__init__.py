@@ -159,6 +159,20 @@ class Engine:
         self.B = B
         return out
 
+    def ar_prefill_multi(self, texts, voice):
+        """U different prompts, one per candidate slot (utterance-batched decode); returns first-step logits [U][8194]"""
+        U = len(texts)
+        arrs = [np.ascontiguousarray(t, dtype=np.int32) for t in texts]
+        i32p = C.POINTER(C.c_int32)
+        ptrs = (i32p * U)(*[a.ctypes.data_as(i32p) for a in arrs])
+        T = np.array([len(a) for a in arrs], dtype=np.int32)
+        voice, vp = _f32(voice)
+        out = np.empty((U, MEL_VOCAB), dtype=np.float32)
+        self.lib.tts_ar_prefill_multi.argtypes = [C.c_void_p, C.c_int32, C.POINTER(i32p), i32p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        self._chk(self.lib.tts_ar_prefill_multi(self.h, U, ptrs, T.ctypes.data_as(i32p), vp, out.ctypes.data_as(C.POINTER(C.c_float))))
+        self.B = U
+        return out
+
     def ar_step(self, tokens, pos_id):
         tokens, tp = _i32(tokens)
         out = np.empty((self.B, MEL_VOCAB), dtype=np.float32)

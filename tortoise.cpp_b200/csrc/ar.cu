@@ -124,6 +124,9 @@ void ar_load(tts_ctx *c, const char *path) {
   const size_t kv = size_t(kLayers) * B * kHeads * s.P * kHeadDim;
   TTS_CUDA_TRY(ctx_malloc(c, &s.kc, kv * 2));
   TTS_CUDA_TRY(ctx_malloc(c, &s.vc, kv * 2));
+  // (utterance batching leaves padding rows in front of a right-aligned prompt: never read, kept finite anyway)
+  TTS_CUDA_TRY(cudaMemsetAsync(s.kc, 0, kv * 2, c->stream));
+  TTS_CUDA_TRY(cudaMemsetAsync(s.vc, 0, kv * 2, c->stream));
   TTS_CUDA_TRY(ctx_malloc(c, &s.d_tokens, B * 4));
   TTS_CUDA_TRY(ctx_malloc(c, &s.d_state, 16));
   TTS_CUDA_TRY(ctx_malloc_host(c, &s.h_tokens, B * 4));
@@ -350,6 +353,8 @@ static void launch_mega4(tts_ctx *c, int B, int n_past, int pos_id) {
   a.logits = s.logits; a.kc = s.kc; a.vc = s.vc;
   a.B = B; a.Bmax = s.Bmax; a.P = s.P; a.n_past = n_past; a.pos_id = pos_id;
   a.n_prefix = s.n_prefix;
+  if (s.multi)
+    for (int b = 0; b < 16; ++b) a.start[b] = s.start[b];
   a.epoch = ++m.mega_epoch;
   a.nrep = 2;
   if (B <= 8) launch_mega4_bt<8>(c, a);
@@ -380,7 +385,7 @@ static void ensure_rows(tts_ctx *c, size_t rows) {
 
 // 30 transformer layers over nb sequences of R rows each (H in/out).  If kv_B > 0 the
 // K/V rows (single sequence) are also scattered into the decode cache of kv_B candidates.
-static void enqueue_rows_layers(tts_ctx *c, const Launcher &L, int nb, int R, int kv_B) {
+static void enqueue_rows_layers(tts_ctx *c, const Launcher &L, int nb, int R, int kv_B, int kv_slot0 = 0, int kv_pos_off = 0) {
   ArModel &m = c->ar;
   ArState &s = c->ars;
   const int rows = nb * R;
@@ -393,7 +398,7 @@ static void enqueue_rows_layers(tts_ctx *c, const Launcher &L, int nb, int R, in
                  3072, 0, E_BIAS_H16);
     if (kv_B > 0)
       L(ar_kv_scatter_kernel, dim3(R), dim3(256), 0, (const float *)s.QKV, s.kc + i * layer_kv,
-        s.vc + i * layer_kv, R, kv_B, s.P);
+        s.vc + i * layer_kv, R, kv_B, s.P, kv_slot0, kv_pos_off);
     L(ar_attn_causal_kernel, dim3((R + 15) / 16, kHeads, nb), dim3(128), 0, (const float *)s.QKV, s.ATThi,
       s.ATTlo, R);
     launch_tgemm(c, L, s.ATThi, s.ATTlo, l.proj_hi, l.proj_lo, l.b_proj, s.H, nullptr, nullptr, rows, kDim, kDim,
@@ -448,6 +453,61 @@ void ar_prefill(tts_ctx *c, const int32_t *text, int T, const float *voice, int 
   s.T = T;
   s.n_past = R;
   s.n_prefix = shared ? R : 0;
+  s.multi = false;
+}
+
+// Utterance batching of the decode loop (BASELINE configs[4]): U DIFFERENT prompts occupy the candidate slots of one
+// batched decode launch (ar_mega4.cuh).  Each prompt is prefilled on its own (the reference's prefill graph, one
+// sequence); its K/V rows go to slot u RIGHT-ALIGNED at rows [Rmax - R_u, Rmax), so that every slot appends its
+// generated rows at the same index and only the attention's first key differs per slot (Mega4Args::start).
+// logits_out [U][8194]: each prompt's first-step logits.  The reference has no counterpart (one prompt per run).
+void ar_prefill_multi(tts_ctx *c, int U, const int32_t *const *text, const int32_t *T, const float *voice, float *logits_out) {
+  ArModel &m = c->ar;
+  ArState &s = c->ars;
+  if (!m.loaded) throw ArgError("AR model not loaded");
+  if (U < 1 || U > s.Bmax || U > 16) throw ArgError("utterance batch exceeds max_batch (<= 16)", TTS_ELIMIT);
+  if (!(c->use_mega && m.dtype == TTS_DTYPE_F16 && s.P <= 1024 && m.l4_h != nullptr))
+    throw ArgError("utterance-batched decode needs the f16 batched decode kernel (dtype f16, max_batch >= 5, max_positions <= 1024)");
+  int Rmax = 0;
+  for (int u = 0; u < U; ++u) {
+    if (T[u] < 1 || T[u] > 404) throw ArgError("text longer than the 404 text positions (main.cpp:685-689)", TTS_ELIMIT);
+    for (int j = 0; j < T[u]; ++j)
+      if (text[u][j] < 0 || text[u][j] > 255) throw ArgError("text token out of range");
+    Rmax = std::max(Rmax, T[u] + 2);
+  }
+  if (Rmax >= s.P) throw ArgError("prompt does not fit max_positions", TTS_ELIMIT);
+  ensure_rows(c, Rmax);
+  Launcher L{c->stream, c->use_pdl, &c->launches};
+  TTS_CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.d_voice, voice, kDim * 4, cudaMemcpyHostToDevice, c->stream));
+  s.h_tokens[0] = TTS_MEL_START;
+  s.h_state[0] = 0;
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.d_tokens, s.h_tokens, 4, cudaMemcpyHostToDevice, c->stream));
+  TTS_CUDA_TRY(cudaMemcpyAsync(s.d_state, s.h_state, 4, cudaMemcpyHostToDevice, c->stream));
+  for (int u = 0; u < U; ++u) {
+    const int R = T[u] + 2;
+    TTS_CUDA_TRY(cudaMemcpyAsync(s.d_text, text[u], T[u] * 4, cudaMemcpyHostToDevice, c->stream));
+    L(ar_embed_rows_kernel, dim3(R, 1), dim3(256), 0, (const int *)s.d_text, T[u], (const float *)s.d_voice,
+      (const int *)s.d_tokens, (const int *)s.d_state, 1, (const float *)m.text_emb, (const float *)m.text_pos,
+      (const float *)m.mel_emb, (const float *)m.mel_pos, s.H);
+    enqueue_rows_layers(c, L, 1, R, 1, u, Rmax - R);
+    L(bcast_row_kernel, dim3(1), dim3(256), 0, (const float *)(s.H + size_t(R - 1) * kDim), s.h + size_t(u) * kDim, kDim);
+    s.start[u] = Rmax - R;
+  }
+  for (int u = U; u < 16; ++u) s.start[u] = 0;
+  enqueue_lm_head(c, L, U);
+  if (logits_out)
+    TTS_CUDA_TRY(cudaMemcpyAsync(s.h_logits, s.logits, size_t(U) * kMelVocab * 4, cudaMemcpyDeviceToHost, c->stream));
+  TTS_CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  TTS_CUDA_TRY(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  c->total_ms += c->last_ms;
+  if (logits_out) memcpy(logits_out, s.h_logits, size_t(U) * kMelVocab * 4);
+  s.B = U;
+  s.T = Rmax - 2;
+  s.n_past = Rmax;
+  s.n_prefix = 0;
+  s.multi = true;
 }
 
 static void build_step_graph(tts_ctx *c, int B) {
@@ -499,7 +559,7 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
   // the pinned token / state words are read by copies queued on the stream (captured in the per-op
   // graph): a back-to-back asynchronous step must not overwrite them before the previous one ran
   const bool mega = c->use_mega && s.P <= 1024;
-  if (s.n_prefix > 0 && !mega) throw ArgError("internal: shared-prefix KV needs the persistent decode kernel");
+  if ((s.n_prefix > 0 || s.multi) && !mega) throw ArgError("internal: shared-prefix / multi-prompt KV needs the persistent decode kernel");
   if (!sync_out && !mega) TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
   for (int b = 0; b < B; ++b) s.h_tokens[b] = tokens[b];
   s.h_state[0] = s.n_past;
@@ -513,7 +573,7 @@ void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, b
       TTS_CUDA_TRY(cudaGetLastError());
       c->launches += 1;
     }
-    if (s.n_prefix > 0) launch_mega4(c, B, s.n_past, pos_id);
+    if (s.n_prefix > 0 || s.multi) launch_mega4(c, B, s.n_past, pos_id);
     else if (c->ar.dtype == TTS_DTYPE_F16) launch_mega2_t<__half>(c, B, s.n_past, pos_id);
     else launch_mega2_t<float>(c, B, s.n_past, pos_id);
     if (logits_out)

@@ -276,10 +276,10 @@ static __global__ void __launch_bounds__(128) ar_attn_causal_kernel(const float 
   }
 }
 
-// Copy K,V of the prefill rows into every candidate's f16 cache:
-// QKV [R][3072] (single shared sequence) -> kc/vc[b][head][pos][64] for b < B.
+// Copy K,V of the prefill rows into the f16 cache of candidate slots [slot0, slot0 + B):
+// QKV [R][3072] (single shared sequence) -> kc/vc[slot][head][pos_off + pos][64].
 static __global__ void __launch_bounds__(256) ar_kv_scatter_kernel(const float *QKV, __half *kc, __half *vc, int R,
-                                                            int B, int P) {
+                                                            int B, int P, int slot0, int pos_off) {
   pdl_launch_dependents();
   pdl_wait();
   const int pos = blockIdx.x;
@@ -288,7 +288,7 @@ static __global__ void __launch_bounds__(256) ar_kv_scatter_kernel(const float *
     const __half v = __float2half_rn(QKV[size_t(pos) * 3072 + 2048 + i]);
     const int head = i / kHeadDim, d = i % kHeadDim;
     for (int b = 0; b < B; ++b) {
-      const size_t idx = ((size_t(b) * kHeads + head) * P + pos) * kHeadDim + d;
+      const size_t idx = ((size_t(slot0 + b) * kHeads + head) * P + pos_off + pos) * kHeadDim + d;
       kc[idx] = k;
       vc[idx] = v;
     }

@@ -63,6 +63,9 @@ struct Mega4Args {
   __half *kc, *vc;  // [30][Bmax][16][P][64]
   int B, Bmax, P, n_past, pos_id;
   int n_prefix;     // K/V rows [0, n_prefix) of every candidate live in candidate slot 0
+  // Utterance batching (slots = DIFFERENT prompts, n_prefix = 0): the prompts are right-aligned in the cache, slot b's
+  // rows [0, start[b]) are padding that attention item (b, head) never looks at.  All zero for candidates of one prompt.
+  int start[16];
   unsigned int epoch;
   int nrep;
 };
@@ -257,17 +260,20 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega4_kernel(M
       cp_async_cg16(vt + r * M2_KV_LD + c * 8, a.vc + off);
     }
   };
+  auto first_tile = [&](int item) { return a.start[item / kHeads] / M2_KV_TILE; };
   auto attention_item = [&](int li, int item, bool prefetched) {
     const int b = item / kHeads, head = item % kHeads;
     const uint32_t tq = tag_of(li, 1);
     const uint2 *qkv = a.ll_qkv + size_t(b) * 3072;
     float Mr = -INFINITY, Lr = 0.f, orun = 0.f;
-    for (int t = 0; t < n_tiles; ++t) {
+    const int start = a.start[b], t0 = start / M2_KV_TILE;  // (the tile of `start` holds a live key: start < n_keys)
+    for (int t = t0; t < n_tiles; ++t) {
       const int j0 = t * M2_KV_TILE, j1 = min(n_keys, j0 + M2_KV_TILE), c = j1 - j0;
+      const int cs = max(start - j0, 0);  // keys [0, cs) of this tile are padding
       const bool has_new = j1 == n_keys;
-      if (t > 0 || !prefetched) prefetch_kv(li, item, t);
+      if (t > t0 || !prefetched) prefetch_kv(li, item, t);
       if (tid < 32) {
-        if (t == 0) {
+        if (t == t0) {
           const float2 v = poll_unit(qkv + head * kHeadDim + 2 * tid, tq);
           qs[2 * tid] = v.x;
           qs[2 * tid + 1] = v.y;
@@ -307,6 +313,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega4_kernel(M
         dot += __shfl_xor_sync(0xffffffffu, dot, 1);
         dot *= 0.125f;
         if (j < c) {
+          if (j < cs) dot = -INFINITY;  // padding: weight exp(-inf) = 0
           if (half == 0) sc[j] = dot;
           lmax = dot;
         }
@@ -328,7 +335,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega4_kernel(M
       bar_consumers();
       {
         float o0 = 0.f, o1 = 0.f;
-        for (int j = warp; j < c; j += GV_WARPS) {
+        for (int j = cs + warp; j < c; j += GV_WARPS) {  // (padding rows may hold anything, NaN included: never read)
           const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(vt + j * M2_KV_LD + 2 * lane));
           const float p = sc[j];
           o0 = fmaf(p, f.x, o0);
@@ -618,7 +625,7 @@ static __global__ void __launch_bounds__(M2_THREADS, 1) ar_decode_mega4_kernel(M
         bar_consumers();
         // first K / V tile of this CTA's attention item: the planes it overwrites were last read by the
         // MMAs above (QKV rows of a CTA are one stage group); lands during the epilogue and the exchange
-        if (p == 0 && !tail && cta < n_items) prefetch_kv(li, cta, 0);
+        if (p == 0 && !tail && cta < n_items) prefetch_kv(li, cta, first_tile(cta));
         // ---------------- epilogue ----------------
         const int ncand = k4 ? 8 : BT;  // candidates covered by the partial tiles of this pass
         for (int e0 = 0; e0 < grows * ncand; e0 += M2_CONSUMERS) {

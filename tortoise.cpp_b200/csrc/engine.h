@@ -63,6 +63,8 @@ struct ArState {
   int Bmax = 0, P = 0;
   int B = 0, T = 0, n_past = 0;
   int n_prefix = 0;  // > 0: the prompt's K/V rows are stored once, in candidate slot 0 (ar_mega4.cuh)
+  bool multi = false;  // slots hold DIFFERENT prompts (utterance batching), right-aligned: slot b's rows [0, start[b]) are padding
+  int start[16] = {0};
   float *h = nullptr, *q = nullptr, *attn = nullptr, *m = nullptr, *logits = nullptr;
   __half *kc = nullptr, *vc = nullptr;  // [30][Bmax][16][P][64]
   int *d_tokens = nullptr, *d_state = nullptr;
@@ -150,6 +152,7 @@ inline void ctx_free_all(tts_ctx *c) {
 // implemented in ar.cu
 void ar_load(tts_ctx *c, const char *path);
 void ar_prefill(tts_ctx *c, const int32_t *text, int T, const float *voice, int B, float *logits_out);
+void ar_prefill_multi(tts_ctx *c, int U, const int32_t *const *text, const int32_t *T, const float *voice, float *logits_out);
 void ar_step(tts_ctx *c, const int32_t *tokens, int pos_id, float *logits_out, bool sync_out);
 void ar_step_topk(tts_ctx *c, const int32_t *tokens, int pos_id, float *vals_out, int32_t *idx_out, int32_t *flags_out);
 void ar_logits(tts_ctx *c, float *logits_out);

@@ -130,6 +130,90 @@ int tts_host_autoregressive(struct tts_ctx *ctx, tts_rng *rng, const int32_t *to
   return TTS_OK;
 }
 
+// Utterance-batched decode loop (BASELINE configs[4]; no reference counterpart: the reference decodes one prompt per
+// run): U different prompts share every batched decode launch, each with its own RNG stream, repetition-penalty
+// window and stop state -- utterance u's codes are what tts_host_autoregressive(B = 1) would sample for it from the
+// same logits.  The latent pass is left to the caller (tts_host_latents per utterance).
+int tts_host_autoregressive_multi(struct tts_ctx *ctx, tts_rng *const *rngs, int U, const int32_t *const *tokens, const int32_t *T,
+                                  const float *voice, const int32_t *forced_codes, int max_steps, int32_t *codes_out,
+                                  int32_t *n_latents, int32_t *steps_out) {
+  if (!ctx || !rngs || !tokens || !T || !voice || !codes_out || !n_latents || U < 1 || U > 16) return TTS_EINVAL;
+  const int V = TTS_MEL_VOCAB, STOP = TTS_MEL_STOP;
+  std::vector<float> logits(size_t(U) * V);
+  int rc = tts_ar_prefill_multi(ctx, U, tokens, T, voice, logits.data());
+  if (rc != TTS_OK) return rc;
+  std::vector<std::vector<int32_t>> prev(U), seqs(U);
+  for (int u = 0; u < U; ++u) {
+    if (!rngs[u]) return TTS_EINVAL;
+    prev[u].assign(size_t(T[u]) + 2, 1);  // [1] * (T + 1) + [8192] (main.cpp:5095-5105)
+    prev[u].back() = TTS_MEL_START;
+  }
+  std::vector<int32_t> samples(U), steps(U, 0);
+  std::vector<char> done(U, 0);
+  std::vector<float> top_v(size_t(U) * TTS_AR_TOPK);
+  std::vector<int32_t> top_i(size_t(U) * TTS_AR_TOPK), top_f(U, 0);
+  bool sparse = false, have_full = true;
+  int i = 0;
+  for (;;) {
+    for (int u = 0; u < U; ++u) {
+      if (done[u]) {
+        samples[u] = STOP;
+        continue;
+      }
+      const int forced = forced_codes ? forced_codes[u] : 0;
+      const bool suppress_stop = forced > 0 && i < forced;
+      float lp = 0.f;
+      int smp = -1;
+      if (sparse && !top_f[u]) {
+        float tv[TTS_AR_TOPK];
+        int32_t ti[TTS_AR_TOPK];
+        int n = 0;
+        for (int k = 0; k < TTS_AR_TOPK; ++k) {
+          const int32_t id = top_i[size_t(u) * TTS_AR_TOPK + k];
+          if (suppress_stop && id == STOP) continue;
+          tv[n] = top_v[size_t(u) * TTS_AR_TOPK + k];
+          ti[n++] = id;
+        }
+        smp = tts_host::sample_sparse_one(rngs[u]->r, tv, ti, n, prev[u].data(), int(prev[u].size()), &lp);
+      }
+      if (smp < 0) {
+        if (!have_full) {
+          rc = tts_ar_logits(ctx, logits.data());
+          if (rc != TTS_OK) return rc;
+          have_full = true;
+        }
+        float *row = logits.data() + size_t(u) * V;
+        if (suppress_stop) row[STOP] = -1e30f;
+        smp = tts_host::sample_one(rngs[u]->r, row, prev[u].data(), int(prev[u].size()), &lp);
+      }
+      if (forced > 0 && i >= forced) smp = STOP;
+      samples[u] = smp;
+      seqs[u].push_back(smp);
+      steps[u] = i + 1;
+      if (smp == STOP) done[u] = 1;
+      prev[u].assign(1, smp);
+      if (seqs[u].size() > 500) return TTS_ELIMIT;  // apply_padding asserts <= 500 (main.cpp:4517)
+    }
+    bool finished = true;
+    for (int u = 0; u < U; ++u) finished = finished && done[u];
+    if (finished) break;
+    if (max_steps > 0 && i + 1 >= max_steps) return TTS_ELIMIT;
+    rc = tts_ar_step_topk(ctx, samples.data(), i + 2, top_v.data(), top_i.data(), top_f.data());  // fixed_position = i + 2
+    if (rc != TTS_OK) return rc;
+    sparse = true;
+    have_full = false;
+    i += 1;
+  }
+  for (int u = 0; u < U; ++u) {
+    tts_host::apply_padding(seqs[u]);
+    if (seqs[u].size() != 502) return TTS_ELIMIT;
+    memcpy(codes_out + size_t(u) * 500, seqs[u].data() + 1, 500 * 4);  // trim_latents drops first / last
+    n_latents[u] = tts_host::trim_count(codes_out + size_t(u) * 500);
+    if (steps_out) steps_out[u] = steps[u];
+  }
+  return TTS_OK;
+}
+
 int tts_host_latents(struct tts_ctx *ctx, const int32_t *tokens, int T, const float *voice, const int32_t *codes500,
                      float *latents_out, int32_t *n_latents) {
   if (!ctx || !tokens || !voice || !codes500 || !latents_out || !n_latents) return TTS_EINVAL;

@@ -107,6 +107,11 @@ int tts_load_vocoder(tts_ctx *c, const char *path) { TTS_API_BODY(c, if (!path) 
 int tts_ar_prefill(tts_ctx *c, const int32_t *text, int32_t T, const float *voice, int32_t B, float *logits) {
   TTS_API_BODY(c, if (!text || !voice) throw tts::ArgError("null argument"); tts::ar_prefill(c, text, T, voice, B, logits))
 }
+int tts_ar_prefill_multi(tts_ctx *c, int32_t U, const int32_t *const *text, const int32_t *T, const float *voice, float *logits) {
+  TTS_API_BODY(c, if (!text || !T || !voice) throw tts::ArgError("null argument");
+               for (int u = 0; u < U; ++u) if (!text[u]) throw tts::ArgError("null argument");
+               tts::ar_prefill_multi(c, U, text, T, voice, logits))
+}
 int tts_ar_step(tts_ctx *c, const int32_t *tokens, int32_t pos_id, float *logits) {
   TTS_API_BODY(c, if (!tokens) throw tts::ArgError("null argument"); tts::ar_step(c, tokens, pos_id, logits, true))
 }

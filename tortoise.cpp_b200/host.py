@@ -54,6 +54,7 @@ class HostLib:
                                                     f32p, i32p]
             lib.tts_host_diffusion.argtypes = [vp, vp, f32p, i32, i32, f32p, i32p]
             lib.tts_host_latents.argtypes = [vp, i32p, i32, f32p, i32p, f32p, i32p]
+            lib.tts_host_autoregressive_multi.argtypes = [vp, P(vp), i32, P(i32p), i32p, f32p, i32p, i32, i32p, i32p, i32p]
             lib.tts_host_diffusion_batch.argtypes = [vp, P(vp), i32, P(f32p), i32p, i32, P(f32p), i32p]
             lib.tts_host_vocoder.argtypes = [vp, vp, f32p, i32, f32p]
         self.lib = lib
@@ -182,6 +183,28 @@ class HostLib:
         if rc != 0:
             raise RuntimeError(f"tts_host_autoregressive failed ({rc}): {engine.lib.tts_last_error(engine.h).decode()}")
         return codes, lat, nlat, score, steps.value
+
+    def autoregressive_multi(self, engine, rngs, tokens_list, voice, forced_codes=None, max_steps=0):
+        """utterance-batched decode loop: U prompts on one batched decode launch per step.
+        Returns (codes [U][500], n_latents [U], steps [U]); latents per utterance via latents()."""
+        assert self.full
+        U = len(tokens_list)
+        arrs = [np.ascontiguousarray(t, dtype=np.int32) for t in tokens_list]
+        i32p, f32p = C.POINTER(C.c_int32), C.POINTER(C.c_float)
+        tok_p = (i32p * U)(*[a.ctypes.data_as(i32p) for a in arrs])
+        T = np.array([len(a) for a in arrs], dtype=np.int32)
+        rng_p = (C.c_void_p * U)(*[r.h for r in rngs])
+        voice = np.ascontiguousarray(voice, dtype=np.float32)
+        forced = None if forced_codes is None else np.ascontiguousarray(forced_codes, dtype=np.int32)
+        codes = np.empty((U, 500), dtype=np.int32)
+        nlat = np.empty(U, dtype=np.int32)
+        steps = np.empty(U, dtype=np.int32)
+        rc = self.lib.tts_host_autoregressive_multi(engine.h, rng_p, U, tok_p, T.ctypes.data_as(i32p), voice.ctypes.data_as(f32p),
+                                                    forced.ctypes.data_as(i32p) if forced is not None else None, max_steps,
+                                                    codes.ctypes.data_as(i32p), nlat.ctypes.data_as(i32p), steps.ctypes.data_as(i32p))
+        if rc != 0:
+            raise RuntimeError(f"tts_host_autoregressive_multi failed ({rc}): {engine.lib.tts_last_error(engine.h).decode()}")
+        return codes, nlat, steps
 
     def latents(self, engine, tokens, voice, codes500):
         """latent pass + trim for one candidate: returns [n][1024]"""
