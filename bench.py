@@ -103,7 +103,10 @@ def measured_peaks():
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one decode-step launch, read from the committed
     `ncu --set full` capture (the decode kernel is unchanged since)"""
-    path = os.path.join(ROOT, "profiles", "r01e_mega3_ncu_full_raw.csv")
+    name = "r02q_mega3_ncu_full_raw.csv"
+    if not os.path.exists(os.path.join(ROOT, "profiles", name)):
+        name = "r01e_mega3_ncu_full_raw.csv"
+    path = os.path.join(ROOT, "profiles", name)
     try:
         with open(path) as f:
             rows = list(csv.reader(f))
@@ -114,7 +117,7 @@ def ncu_traffic():
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         rd = np.mean([float(r[ir].replace(",", "")) for r in vals]) * scale.get(units[ir], 1.0)
         wr = np.mean([float(r[iw].replace(",", "")) for r in vals]) * scale.get(units[iw], 1.0)
-        return int(rd + wr), "profiles/r01e_mega3_ncu_full_raw.csv (ar_decode_mega3_kernel<1>, ~20 cached positions)"
+        return int(rd + wr), f"profiles/{name} (ar_decode_mega3_kernel<1>, ~20 cached positions)"
     except Exception as e:  # the capture is evidence, not a dependency of the measurement
         return None, f"unavailable: {e}"
 
