@@ -3,6 +3,8 @@
 // TIME-MAJOR ([seq][t][channel], channel fastest) -- the transpose of the reference's
 // [channel][t] -- so that every 1x1 / k3 convolution is a K-contiguous implicit GEMM.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tts {
@@ -231,7 +233,7 @@ static __global__ void silu_split_kernel(const float *in, __half *hi, __half *lo
 constexpr int TA_BK = 64, TA_LD = kHeadDim + 8;  // 72 halves per row: ldmatrix rows fall on distinct banks
 template <int NW>
 constexpr size_t ta_smem_bytes(int T) {
-  return size_t(4 * TA_BK) * TA_LD * sizeof(__half) + size_t(T + 16 * NW) * sizeof(float) + 32 * sizeof(float);
+  return size_t(4 * TA_BK) * TA_LD * sizeof(__half) + size_t(T + 16 * NW + TA_BK) * sizeof(float) + 32 * sizeof(float);
 }
 __device__ __forceinline__ void ta_cp16(void *dst, const void *src, bool valid) {
   const int n = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
@@ -251,6 +253,13 @@ __device__ __forceinline__ void ta_mma(float (&d)[4], const uint32_t (&a)[4], ui
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 2^x for x <= 0 (softmax weights): one MUFU.EX2; exp2f() wraps it in a range fix-up (compare + two multiplies) that
+// only matters for |x| > 126, where flushing to zero is what a softmax weight should do anyway
+__device__ __forceinline__ float ta_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ uint32_t ta_pack(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -340,34 +349,51 @@ static __global__ void __launch_bounds__(NW * 32, NW == 4 ? 5 : 8) diff_attn_tc_
     }
     const int k0 = kt * TA_BK;
     float mx_lo = -INFINITY, mx_hi = -INFINITY;
+    {
+      // bias of (row g, key j) = btp[j - k0 - 2 t4]; row g + 8 sits 8 entries lower: ITS bias at key tile nt is row g's
+      // at key tile nt - 1, so each entry is fetched once (18 loads per tile instead of 32).  The table has TA_BK
+      // entries of slack behind T + BQ - 1: a partial last tile reads (and then masks) past the live part.
+      const float *btp = bt + k0 + 2 * t4 + boff;
+      auto scores = [&](auto masked) {
+        float p0 = btp[-8], p1 = btp[-7];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = k0 + nt * 8 + 2 * t4 + e;
-        const bool ok = j < T;
-        const float a = ok ? fmaf(s[nt][e], 0.125f * kLog2e, bt[j + boff]) : -INFINITY;
-        const float b = ok ? fmaf(s[nt][2 + e], 0.125f * kLog2e, bt[j + boff - 8]) : -INFINITY;
-        s[nt][e] = a;
-        s[nt][2 + e] = b;
-        mx_lo = fmaxf(mx_lo, a);
-        mx_hi = fmaxf(mx_hi, b);
-      }
+        for (int nt = 0; nt < 8; ++nt) {
+          const float b0 = btp[nt * 8], b1 = btp[nt * 8 + 1];
+          float a0 = fmaf(s[nt][0], 0.125f * kLog2e, b0), a1 = fmaf(s[nt][1], 0.125f * kLog2e, b1);
+          float a2 = fmaf(s[nt][2], 0.125f * kLog2e, p0), a3 = fmaf(s[nt][3], 0.125f * kLog2e, p1);
+          p0 = b0;
+          p1 = b1;
+          if (decltype(masked)::value) {
+            const int j = k0 + nt * 8 + 2 * t4;
+            if (j >= T) a0 = a2 = -INFINITY;
+            if (j + 1 >= T) a1 = a3 = -INFINITY;
+          }
+          s[nt][0] = a0;
+          s[nt][1] = a1;
+          s[nt][2] = a2;
+          s[nt][3] = a3;
+          mx_lo = fmaxf(mx_lo, fmaxf(a0, a1));
+          mx_hi = fmaxf(mx_hi, fmaxf(a2, a3));
+        }
+      };
+      // every key of the tile exists (all tiles but the last): no masks -- a real branch, not predication
+      if (k0 + TA_BK <= T) scores(std::false_type{});
+      else scores(std::true_type{});
     }
     mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
     mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
     mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
     mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
     const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);  // finite: key k0 is always valid
-    const float c_lo = exp2f(m_lo - mn_lo), c_hi = exp2f(m_hi - mn_hi);
+    const float c_lo = ta_ex2(m_lo - mn_lo), c_hi = ta_ex2(m_hi - mn_hi);
     m_lo = mn_lo;
     m_hi = mn_hi;
     float ps_lo = 0.f, ps_hi = 0.f;
     uint32_t pf[4][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f(s[nt][0] - mn_lo), p1 = exp2f(s[nt][1] - mn_lo);
-      const float p2 = exp2f(s[nt][2] - mn_hi), p3 = exp2f(s[nt][3] - mn_hi);
+      const float p0 = ta_ex2(s[nt][0] - mn_lo), p1 = ta_ex2(s[nt][1] - mn_lo);
+      const float p2 = ta_ex2(s[nt][2] - mn_hi), p3 = ta_ex2(s[nt][3] - mn_hi);
       ps_lo += p0 + p1;
       ps_hi += p2 + p3;
       pf[nt >> 1][(nt & 1) * 2] = ta_pack(p0, p1);
