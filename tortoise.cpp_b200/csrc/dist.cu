@@ -111,6 +111,33 @@ int tts_group_init_local(tts_ctx **ctxs, int n, tts_group **out) {
   if (nccl().CommInitAll(g->comm.data(), n, devs.data()) != ncclSuccess) { delete g; return TTS_ECUDA; }
   g->d_send.assign(n, nullptr);
   g->d_recv.assign(n, nullptr);
+  // First collective = connection setup (seconds): pay it here, on streams of our own, so that a caller who builds
+  // the group in the background (the CLI does, while models load) finds tts_gather_select warm.
+  {
+    std::vector<cudaStream_t> st(n, nullptr);
+    std::vector<int32_t *> snd(n, nullptr), rcv(n, nullptr);
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) {
+      ok = cudaSetDevice(devs[i]) == cudaSuccess && cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaMalloc(&snd[i], 8) == cudaSuccess && cudaMalloc(&rcv[i], size_t(n) * 8) == cudaSuccess &&
+           cudaMemsetAsync(snd[i], 0, 8, st[i]) == cudaSuccess;
+    }
+    if (ok) {
+      ok = nccl().GroupStart() == ncclSuccess;
+      for (int i = 0; i < n && ok; ++i) {
+        cudaSetDevice(devs[i]);
+        ok = nccl().AllGather(snd[i], rcv[i], 2, ncclInt32, g->comm[i], st[i]) == ncclSuccess;
+      }
+      ok = nccl().GroupEnd() == ncclSuccess && ok;
+    }
+    for (int i = 0; i < n; ++i) {
+      cudaSetDevice(devs[i]);
+      if (st[i]) { cudaStreamSynchronize(st[i]); cudaStreamDestroy(st[i]); }
+      if (snd[i]) cudaFree(snd[i]);
+      if (rcv[i]) cudaFree(rcv[i]);
+    }
+    if (!ok) { cudaGetLastError(); tts_group_free(g); return TTS_ECUDA; }
+  }
   *out = g;
   return TTS_OK;
 }

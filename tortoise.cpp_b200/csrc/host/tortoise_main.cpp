@@ -6,7 +6,8 @@
 // numbers / symbols and lower-case the message before tokenisation), --gpus G (shard the
 // candidates over G GPUs of this box: one context + one host thread per GPU, weights replicated,
 // ONE NCCL all-gather of (score, length) per candidate for the selection -- tts_gather_select --
-// then latent pass + diffusion + vocoder for the winner on the GPU that owns it).
+// then latent pass + diffusion + vocoder for the winner on the GPU that owns it; the communicators are
+// built in a background thread while the models load and the candidates decode).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -78,15 +79,38 @@ int main(int argc, char **argv) {
   std::vector<tts_ctx *> ctxs(gpus, nullptr);
   const double t0 = now_s();
   std::vector<int> load_rc(gpus, TTS_OK);
-  auto load_one = [&](int g) {
+  for (int g = 0; g < gpus; ++g) {
     tts_config cfg{};
     cfg.device = device + g;
     cfg.dtype = dtype;
     cfg.max_batch = per > 4 ? per : 4;
     cfg.max_positions = 404 + (per > 4 ? 256 : 0);
     cfg.parity_quirks = 1;
-    int rc = tts_init(&cfg, &ctxs[g]);
-    if (rc == TTS_OK) rc = tts_load_ar(ctxs[g], (models + "/ggml-model.bin").c_str());
+    load_rc[g] = tts_init(&cfg, &ctxs[g]);
+    if (load_rc[g] != TTS_OK) {
+      fprintf(stderr, "GPU %d: %s\n", device + g, tts_last_error(nullptr));
+      return 1;
+    }
+  }
+  // the NCCL communicators of the selection step are built in the background while the models load and the
+  // candidates decode: ncclCommInitAll over 8 GPUs takes tens of seconds on some hosts (topology probing), the
+  // decode loop of 8 candidates per GPU well under one
+  tts_group *grp = nullptr;
+  int grp_rc = TTS_OK;
+  double grp_s = 0.0;
+  std::thread grp_thread;
+  if (gpus > 1)
+    grp_thread = std::thread([&] {
+      const double g0 = now_s();
+      grp_rc = tts_group_init_local(ctxs.data(), gpus, &grp);
+      grp_s = now_s() - g0;
+    });
+  struct Joiner {  // every early return below leaves through here
+    std::thread &t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } joiner{grp_thread};
+  auto load_one = [&](int g) {
+    int rc = tts_load_ar(ctxs[g], (models + "/ggml-model.bin").c_str());
     if (rc == TTS_OK) rc = tts_load_diffusion(ctxs[g], (models + "/ggml-diffusion-model.bin").c_str());
     if (rc == TTS_OK) rc = tts_load_vocoder(ctxs[g], (models + "/ggml-vocoder-model.bin").c_str());
     load_rc[g] = rc;
@@ -100,6 +124,7 @@ int main(int argc, char **argv) {
   for (int g = 0; g < gpus; ++g)
     if (load_rc[g] != TTS_OK) {
       fprintf(stderr, "GPU %d: %s\n", device + g, ctxs[g] ? tts_last_error(ctxs[g]) : tts_last_error(nullptr));
+      if (grp_thread.joinable()) grp_thread.join();
       return 1;
     }
   const double t1 = now_s();
@@ -134,9 +159,12 @@ int main(int argc, char **argv) {
   // selection.  The reference diffuses candidate 0 (main.cpp:6575); with more candidates the best mean
   // log-probability wins (extension; identical for one candidate).  Across GPUs: one NCCL all-gather.
   int owner = 0, best = 0;
+  const double t_ar = now_s();  // the decode loops of every GPU are done
+  double wait_grp_s = 0.0;
   if (gpus > 1) {
-    tts_group *grp = nullptr;
-    if (tts_group_init_local(ctxs.data(), gpus, &grp) != TTS_OK) { fprintf(stderr, "NCCL group init failed\n"); return 1; }
+    grp_thread.join();
+    wait_grp_s = now_s() - t_ar;
+    if (grp_rc != TTS_OK) { fprintf(stderr, "NCCL group init failed\n"); return 1; }
     std::vector<float> sc(size_t(gpus) * B);
     std::vector<int32_t> ln(size_t(gpus) * B);
     for (int g = 0; g < gpus; ++g)
@@ -184,10 +212,13 @@ int main(int argc, char **argv) {
   printf("WAV file saved successfully. :^)\n");
   if (bench_json) {
     const double audio_s = audio.size() / 24000.0;
-    printf("{\"load_s\": %.3f, \"ar_s\": %.4f, \"diffusion_s\": %.4f, \"vocoder_s\": %.4f, \"audio_s\": %.3f, "
+    // ar_s: the decode loops (all GPUs in parallel); select_s: all-gather + argmax + the winner's latent pass;
+    // nccl_init_s: communicator construction (runs beside load + decode), nccl_wait_s: what of it was NOT hidden
+    printf("{\"load_s\": %.3f, \"ar_s\": %.4f, \"select_s\": %.4f, \"nccl_init_s\": %.3f, \"nccl_wait_s\": %.3f, "
+           "\"diffusion_s\": %.4f, \"vocoder_s\": %.4f, \"audio_s\": %.3f, "
            "\"rtf\": %.3f, \"ar_steps\": %d, \"candidates\": %d, \"winner\": %d, \"launches\": %lld, \"codes\": [",
-           t1 - t0, t2 - t1, t3 - t2, t4 - t3, audio_s, audio_s / (t4 - t1), ar_steps, candidates, owner * B + best,
-           (long long)tts_launch_count(ctx));
+           t1 - t0, t_ar - t1, t2 - t_ar - wait_grp_s, grp_s, wait_grp_s, t3 - t2, t4 - t3, audio_s,
+           audio_s / (t4 - t1 - wait_grp_s), ar_steps, candidates, owner * B + best, (long long)tts_launch_count(ctx));
     // sampled mel codes of the diffused candidate up to and including the stop token (parity tests)
     for (int i = 0; i < 500; ++i) {
       const int code = codes[owner][size_t(best) * 500 + i];
