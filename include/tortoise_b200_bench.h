@@ -20,8 +20,6 @@ int tts_bench_gemv(tts_ctx *ctx, int32_t op, int32_t B, int32_t iters, float *ms
  * (streamed weights + KV read/append + embeddings + logits). */
 int tts_bench_decode_step(tts_ctx *ctx, int32_t iters, float *ms_per_step, double *bytes_per_step);
 
-/* debugging aid: the first n floats of a denoiser activation buffer (0 CW, 1 X, 2 OUT, 3 INP, 4 QKV, 5 H1) */
-int tts_debug_diffusion_buffer(tts_ctx *ctx, int32_t which, float *out, int64_t n);
 
 /* the denoiser's 3-tap convolution (tcgen05 GEMM, M = 2 S rows, N = K = 1024) on the loaded diffusion
  * weights: `iters` back-to-back launches between two CUDA events; ms per launch and FLOP per launch */

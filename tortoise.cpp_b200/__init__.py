@@ -93,7 +93,6 @@ def load_library() -> C.CDLL:
     lib.tts_group_free.restype = None
     lib.tts_bench_decode_step.argtypes = [vp, i32, P(C.c_float), P(C.c_double)]
     lib.tts_bench_gemv.argtypes = [vp, i32, i32, i32, P(C.c_float), P(C.c_double)]
-    lib.tts_debug_diffusion_buffer.argtypes = [vp, i32, f32p, C.c_int64]
     lib.tts_bench_conv3.argtypes = [vp, i32, i32, P(C.c_float), P(C.c_double)]
     _lib = lib
     return lib
@@ -260,11 +259,6 @@ class Engine:
         ms, by = C.c_float(), C.c_double()
         self._chk(self.lib.tts_bench_decode_step(self.h, iters, C.byref(ms), C.byref(by)))
         return ms.value, by.value
-
-    def debug_buffer(self, which, n):
-        out = np.empty(n, dtype=np.float32)
-        self._chk(self.lib.tts_debug_diffusion_buffer(self.h, which, out.ctypes.data_as(C.POINTER(C.c_float)), n))
-        return out
 
     def bench_conv3(self, S, iters):
         ms, fl = C.c_float(), C.c_double()

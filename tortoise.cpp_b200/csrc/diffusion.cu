@@ -454,15 +454,6 @@ static int count_kernel_nodes(cudaGraph_t graph) {
   return k;
 }
 
-// Debug only (tortoise_b200_bench.h): copy one of the denoiser's activation buffers to the host
-void diff_debug_read(tts_ctx *c, int which, float *out, size_t n) {
-  if (!c->diff) throw ArgError("diffusion model not loaded");
-  DiffModel &m = *c->diff;
-  const float *src = which == 0 ? m.CW : which == 1 ? m.X : which == 2 ? m.OUT : which == 3 ? m.INP : which == 6 ? m.CE : which == 7 ? reinterpret_cast<const float *>(m.ATThi) : m.H1;
-  TTS_CUDA_TRY(cudaStreamSynchronize(c->stream));
-  TTS_CUDA_TRY(cudaMemcpy(out, src, n * 4, cudaMemcpyDeviceToHost));
-}
-
 // Measurement only (tortoise_b200_bench.h): the denoiser's 3-tap convolution -- the GEMM shape the diffusion
 // stage spends most of its time in -- `iters` back-to-back launches on the model's own weights between two
 // CUDA events.  M = 2 S rows (cond + uncond), N = K = 1024.

@@ -174,7 +174,6 @@ void diff_begin_batch(tts_ctx *c, int U, const float *const *latents, const int3
 void diff_step_batch(tts_ctx *c, const float *const *noise_blocks);
 void diff_end_batch(tts_ctx *c, float *const *mel);
 void diff_free(tts_ctx *c);
-void diff_debug_read(tts_ctx *c, int which, float *out, size_t n);
 void diff_bench_conv3(tts_ctx *c, int S, int iters, float *ms, double *flop);
 void voc_load(tts_ctx *c, const char *path);
 void voc_run(tts_ctx *c, const float *mel, int S, const float *noise, float *audio);

@@ -174,9 +174,6 @@ int tts_bench_gemv(tts_ctx *c, int32_t op, int32_t B, int32_t iters, float *ms, 
   TTS_API_BODY(c, if (!ms || !bytes || iters < 1) throw tts::ArgError("bad argument"); tts::ar_bench_gemv(c, op, B, iters, ms, bytes))
 }
 
-int tts_debug_diffusion_buffer(tts_ctx *c, int32_t which, float *out, int64_t n) {
-  TTS_API_BODY(c, if (!out || n < 1) throw tts::ArgError("bad argument"); tts::diff_debug_read(c, which, out, size_t(n)))
-}
 int tts_bench_conv3(tts_ctx *c, int32_t S, int32_t iters, float *ms, double *flop) {
   TTS_API_BODY(c, if (!ms || !flop) throw tts::ArgError("bad argument"); tts::diff_bench_conv3(c, S, iters, ms, flop))
 }
