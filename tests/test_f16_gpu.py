@@ -245,6 +245,26 @@ def test_utterance_batched_decode_vs_oracle(engine_f16, golden, voice, model_dir
     assert same >= 1
 
 
+def test_utterance_batched_decode_two_prompts(engine_f16, golden, voice, model_dir):
+    """fewer prompts than the batched kernel's minimum candidate count (a rank's last batch of configs[4]):
+    U = 2 on the same launch, against the oracle per utterance"""
+    import _pkg
+    import tortoise_oracle as O
+    sw = _pkg.import_sub("synth_weights")
+    W = sw.read_container(os.path.join(model_dir, "ggml-model.bin"))
+    base = [int(t) for t in golden("ar_b1.npz")["tokens"]]
+    texts = [base[:9], base]
+    got = [engine_f16.ar_prefill_multi(texts, voice)]
+    toks = [[4000 + 13 * u + 7 * i for u in range(2)] for i in range(2)]
+    got += [engine_f16.ar_step(toks[i], i + 2) for i in range(2)]
+    for u in range(2):
+        ar = O.AROracle(W, weight_dtype="f16")
+        ref = [ar.prefill(np.array(texts[u]), voice, 1)[0]] + [ar.step(np.array([toks[i][u]]), i + 2)[0] for i in range(2)]
+        errs = [float(np.abs(got[i][u] - ref[i]).max()) for i in range(3)]
+        print(f"U = 2, utterance {u}: max-abs per step {['%.2e' % e for e in errs]}")
+        assert max(errs) < F32_LOGIT_TOL
+
+
 def test_batched_topk_step_is_consistent_with_full_logits(engine_f16, golden, voice):
     """tts_ar_step_topk: the device-side top-64 (value, index) pairs of every candidate equal the
     top-64 of the full logits row of the same step (bit-exact values, same index set)."""
