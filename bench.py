@@ -123,37 +123,55 @@ def ncu_traffic():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """clocks + throttle reasons DURING the timed region, the recipe's way (B200_PROFILING.md): ONE `nvidia-smi
+    --query-gpu=... -lms 200` process for every GPU of the job, started before and terminated after the region
+    (a process per sample -- what round 1 did -- initialises NVML each time and perturbs the ranks it measures)."""
 
-    def __init__(self, index: int):
+    def __init__(self, indices):
         super().__init__(daemon=True)
-        self.index = index
+        self.indices = list(indices)
         self.stop_flag = False
         self.samples = []
         self.reasons = set()
+        self.proc = None
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                f = [x.strip() for x in out.split(",")]
-                self.samples.append((float(f[0]), float(f[1])))
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                                          ",".join(str(i) for i in self.indices)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    self.samples.append((float(f[0]), float(f[1])))
+                except (ValueError, IndexError):
+                    continue
                 for n, v in zip(names, f[2:]):
                     if v.lower().startswith("active"):
                         self.reasons.add(n)
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()  # the exact process this object started
             except Exception:
                 pass
-            time.sleep(0.2)
+        self.join(timeout=3)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm = sorted(s[0] for s in self.samples)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons),
+                "gpus_sampled": self.indices, "samples": len(self.samples)}
 
 
 def prepare_models():
@@ -465,8 +483,9 @@ def main():
         one_utterance(k, 1000 + k)
     eng.sync()
     launches0, dev0 = eng.launch_count, eng.device_ms_total
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(range(world) if world > 1 else [local_rank])  # rank 0 watches every GPU of the job
+    if rank == 0:
+        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -482,8 +501,8 @@ def main():
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - t_start
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.stop()
     launches = eng.launch_count - launches0
     dev_s = (eng.device_ms_total - dev0) / 1e3  # CUDA-event time of every stage call in the region
 
