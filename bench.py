@@ -197,6 +197,13 @@ def c5_prompts(n=256):
     return out
 
 
+def c5_batches(prompts, rank, world, U):
+    """configs[4] sharding: rank r owns utterances u = r (mod world) -- no data-path collective -- sorted by length
+    so that a batch of U pads little; returns the rank's batches (lists of utterance indices)"""
+    mine = sorted(range(rank, len(prompts), world), key=lambda u: (len(prompts[u]), u))
+    return [mine[i:i + U] for i in range(0, len(mine), U)]
+
+
 # ------------------------------------------------------------------------------ reference arm
 def _harness_env():
     if not os.path.exists(HARNESS):
@@ -413,15 +420,15 @@ def main():
     prompts = c5_prompts() if cfg_name == "C5" else None
     U5 = max(1, min(16, args.c5_batch))
     if cfg_name == "C5":  # this rank's share (u mod N), sorted by length so that a batch pads little
-        my_utts = sorted(range(rank, 256, world), key=lambda u: len(prompts[u]))
-        n_batches = (len(my_utts) + U5 - 1) // U5
+        batches = c5_batches(prompts, rank, world, U5)
+        n_batches = len(batches)
 
     def one_batch(k, seed):
         """configs[4]: one step = U utterances of this rank: ONE utterance-batched decode loop (U prompts per decode
         launch), latent pass per utterance, ONE batched diffusion (U utterances of different lengths on one launch
         set per sampling step), vocoder one by one"""
         b = (k * 7) % n_batches  # walk the length buckets rather than only the shortest ones
-        utts = my_utts[b * U5:(b + 1) * U5]
+        utts = batches[b]
         out = dict(ar_wall=0.0, ar_dev_ms=0.0, tokens=0, audio_s=0.0, diff_ms=0.0, voc_ms=0.0, h2d=0, d2h=0, gather_ms=0.0, owner=rank)
         # AR: the U prompts ride on ONE batched decode launch per step (tts_ar_prefill_multi / ar_mega4.cuh), each with
         # its own RNG stream and forced length; then the latent pass per utterance

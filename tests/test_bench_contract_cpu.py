@@ -55,3 +55,35 @@ def test_b200_arm_fails_loudly_without_a_gpu():
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_c5_sharding_partitions_the_utterances():
+    """configs[4]: every utterance lands on exactly one rank and in exactly one batch, batches hold at most U
+    utterances of neighbouring lengths, and the prompt set is the seeded one (20..300 characters)"""
+    sys.path.insert(0, ROOT)
+    import bench
+    prompts = bench.c5_prompts()
+    assert len(prompts) == 256 and all(20 <= len(p) <= 300 for p in prompts)
+    assert prompts == bench.c5_prompts()  # seeded
+    for world in (1, 2, 3, 8):
+        seen = []
+        for rank in range(world):
+            batches = bench.c5_batches(prompts, rank, world, 8)
+            assert all(1 <= len(b) <= 8 for b in batches)
+            assert all(u % world == rank for b in batches for u in b)
+            lens = [len(prompts[u]) for b in batches for u in b]
+            assert lens == sorted(lens)
+            seen += [u for b in batches for u in b]
+        assert sorted(seen) == list(range(256))
+
+
+def test_clock_sampler_summary_without_nvidia_smi():
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler([0, 1])
+    assert s.summary()["reasons"] == ["nvidia-smi unavailable"]
+    s.samples = [(1965.0, 1965.0), (1900.0, 1965.0), (1965.0, 1965.0)]
+    s.reasons = {"sw_power_cap"}
+    out = s.summary()
+    assert out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    assert out["gpus_sampled"] == [0, 1] and out["samples"] == 3
