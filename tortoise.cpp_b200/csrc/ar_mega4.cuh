@@ -1,5 +1,7 @@
 // ar_mega4.cuh -- AR decode step as one persistent kernel for 5..16 candidates on ONE weight stream
-// (f16 weights; BASELINE configs[2]: 16 candidates per GPU, configs[3]: 8 per GPU).
+// (f16 weights; BASELINE configs[2]: 16 candidates per GPU, configs[3]: 8 per GPU), and for 1..16 DIFFERENT
+// utterances in the candidate slots (configs[4], tts_ar_prefill_multi: prompts right-aligned in the KV cache,
+// Mega4Args::start[b] = first live key of slot b; nothing else in the kernel knows the difference).
 //
 // Same math (reference graph autoregressive_graph(fake_inputs=false), main.cpp:2668-3029; candidate
 // batch axis main.cpp:5044) and the same cross-CTA protocol as ar_mega2/3.cuh: (value, tag) pairs
